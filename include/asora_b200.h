@@ -1,0 +1,142 @@
+/*
+ * asora_b200.h -- C ABI of libasora_b200.so: the B200-native (sm_100a) replacement for pyc2ray's
+ * ASORA ray-tracing library and for the per-cell ionisation chemistry pass.
+ *
+ * Every entry point returns 0 on success and a non-zero code on failure; it never throws and never
+ * aborts.  asora_last_error() returns a description of the most recent failure on the calling thread's
+ * process (the reference throws C++ exceptions through extern "C" -> std::terminate:
+ * src/asora/raytracing.cu:134-139, src/asora/memory.cu:70-75).
+ *
+ * One context per process, bound to the CUDA device that is current when asora_device_init() is
+ * called (same ownership model as the reference's process-global pointers, src/asora/memory.cu:20-29).
+ * Not thread-safe; calls are synchronous unless stated otherwise.
+ *
+ * Grid layout everywhere: float64, flat, index i*N*N + j*N + k of the logical cell (i,j,k)
+ * (src/asora/raytracing.cu:30).  Sources: int32[3*NumSrc] interleaved x,y,z, 0-indexed, and
+ * float64[NumSrc] fluxes in units of 1e48 photons/s (pyc2ray/utils/sourceutils.py:30-31).
+ *
+ * Paths cited below are relative to the reference checkout (phirling/pyc2ray).
+ */
+#ifndef ASORA_B200_H
+#define ASORA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- the six libasora entry points (src/asora/python_module.cu:153-161) ------------------------- */
+
+/* replaces libasora.device_init(N, num_src_par): python_module.cu:73-82 -> memory.cu:34-80.
+ * Allocates the density / ionised-fraction / rate grids for mesh size N on the current device.
+ * num_src_par (the reference's source batch size) is accepted for signature compatibility; this
+ * implementation keeps column densities on-chip (or in one L2-resident scratch grid) and does not
+ * allocate N^3 doubles per in-flight source. */
+int asora_device_init(int N, int num_src_par);
+
+/* replaces libasora.device_close(): python_module.cu:87-92 -> memory.cu:119-129.  Frees everything,
+ * including both photo tables (the reference leaks the thick table). */
+int asora_device_close(void);
+
+/* replaces libasora.density_to_device(ndens, N): python_module.cu:97-109 -> memory.cu:85-88. */
+int asora_density_to_device(const double* ndens, int N);
+
+/* replaces libasora.photo_table_to_device(thin, thick, NumTau): python_module.cu:114-128 ->
+ * memory.cu:90-98.  NumTau is the number of doubles in each table.  Re-calling replaces the tables
+ * (the reference leaks the previous allocation). */
+int asora_photo_table_to_device(const double* thin_table, const double* thick_table, int NumTau);
+
+/* replaces libasora.source_data_to_device(pos, flux, NumSrc): python_module.cu:133-148 ->
+ * memory.cu:99-114. */
+int asora_source_data_to_device(const int32_t* pos, const double* flux, int NumSrc);
+
+/* replaces libasora.do_all_sources(R, coldensh_out, sig, dr, ndens, xh_av, phi_ion, NumSrc, m1,
+ * minlogtau, dlogtau, NumTau): python_module.cu:21-68 -> raytracing.cu:79-148.
+ * Copies xh_av (host, N^3) to the device, zeroes the rate grid, ray-traces the first NumSrc uploaded
+ * sources out to radius R (cells), and copies the summed rates into phi_ion (host, N^3).  The
+ * reference ignores its coldensh_out and ndens arguments (raytracing.cu:116), so they are not part
+ * of this ABI.  NumTau has the reference's meaning: the upper clamp of the table index
+ * (rates.cu:78-79); indices are additionally clamped to the uploaded table length. */
+int asora_do_all_sources(double R, double sig, double dr, const double* xh_av, double* phi_ion,
+                         int NumSrc, int N, double minlogtau, double dlogtau, int NumTau);
+
+/* ---- chemistry half of the boundary (f2py libc2ray.chemistry.global_pass) ------------------------ */
+
+/* replaces libc2ray.chemistry.global_pass(dt,ndens,temp,xh,xh_av,xh_intermed,phi_ion,bh00,albpow,
+ * colh0,temph0,abu_c) -> conv_flag: src/c2ray/chemistry.f90:13-48 (+ :53-316).
+ * All arrays are host float64[ncell] sharing one memory order (the update is cell-local).
+ * xh_av and xh_intermed are updated in place.  *conv_flag receives the number of non-converged
+ * cells.  xh, xh_av and xh_intermed may alias each other (pyc2ray/chemistry.py:85,91): all inputs
+ * are read before any output is written; xh_av is stored first, xh_intermed last. */
+int asora_global_pass(double dt, const double* ndens, const double* temp, const double* xh,
+                      double* xh_av, double* xh_intermed, const double* phi_ion, double bh00,
+                      double albpow, double colh0, double temph0, double abu_c, int64_t ncell,
+                      int* conv_flag);
+
+/* ---- device-resident variants (no host<->device traffic; used by the fused evolve loop) --------- */
+
+/* Named device buffers owned by the context (all float64[N^3] unless noted). */
+enum {
+    ASORA_BUF_NDENS = 0,
+    ASORA_BUF_XH_AV = 1,
+    ASORA_BUF_PHI_ION = 2,
+    ASORA_BUF_XH = 3,          /* ionised fraction at the start of the time step */
+    ASORA_BUF_XH_INTERMED = 4, /* end-of-step ionised fraction of the current iteration */
+    ASORA_BUF_TEMP = 5,
+    ASORA_BUF_COLDENS = 6,     /* outgoing column density of the last debug sweep */
+    ASORA_BUF_COUNT = 7
+};
+
+/* Device address of a named buffer (allocated on first use), or NULL on error. */
+void* asora_device_buffer(int which);
+
+/* Host -> device / device -> host copy of a named buffer (N^3 doubles). */
+int asora_buffer_upload(int which, const double* host);
+int asora_buffer_download(int which, double* host);
+
+/* Ray-trace sources [src_begin, src_begin+src_count) of the uploaded list using the device-resident
+ * NDENS and XH_AV buffers; rates are accumulated into PHI_ION, which is zeroed first when
+ * zero_phi != 0.  Asynchronous on the context's stream; asora_sync() waits. */
+int asora_raytrace_device(double R, double sig, double dr, int src_begin, int src_count,
+                          double minlogtau, double dlogtau, int NumTau, int zero_phi);
+
+/* Chemistry pass on the device-resident buffers (NDENS, TEMP, XH, XH_AV, XH_INTERMED, PHI_ION).
+ * Outputs: conv_flag, sum(xh_intermed), sum(1 - xh_intermed) (pyc2ray/evolve.py:210-217), reduced
+ * deterministically on the device.  Synchronous. */
+int asora_global_pass_device(double dt, double bh00, double albpow, double colh0, double temph0,
+                             double abu_c, int* conv_flag, double* sum_xh1, double* sum_xh0);
+
+/* Wait for all work queued on the context's stream. */
+int asora_sync(void);
+
+/* ---- diagnostics -------------------------------------------------------------------------------- */
+
+/* Ray-trace ONE uploaded source and return its outgoing column density grid (host, N^3; cells the
+ * sweep does not visit are 0) -- for column-density parity tests.  phi_ion (host, N^3) may be NULL. */
+int asora_debug_single_source(double R, double sig, double dr, const double* xh_av, int src_index,
+                              double minlogtau, double dlogtau, int NumTau, double* coldensh_out,
+                              double* phi_ion);
+
+/* Force the sweep variant: 0 = automatic, 1 = shared-memory level sweep (one CTA per source batch),
+ * 2 = grid-cooperative level sweep (whole GPU per source).  Returns non-zero for unknown values. */
+int asora_set_sweep_variant(int variant);
+
+/* Statistics of the most recent ray trace: variant used, number of kernel launches, number of
+ * (source, cell) updates, q_max, number of Chebyshev levels, device milliseconds (CUDA events on
+ * the context's stream around the sweep kernel(s) only).  Any pointer may be NULL. */
+int asora_last_sweep_stats(int* variant, int* launches, int64_t* updates, int* q_max, int* levels,
+                           float* kernel_ms);
+
+/* Number of cells the sweep visits per source: |octahedron(q_max) & cube| (raytracing.cu:101,
+ * 122-123,241).  Pure host arithmetic; needs no device. */
+int64_t asora_cells_per_source(int N, double R);
+
+const char* asora_last_error(void);
+const char* asora_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASORA_B200_H */

@@ -1,0 +1,45 @@
+// ref_shim.cu -- extern "C" handles on the reference's own ASORA host functions, so the UNMODIFIED
+// reference CUDA sources (compiled where they lie under /root/reference/src/asora, see ref_build.py)
+// can be driven through ctypes on the GPU box.  Test infrastructure only: this is the "kernel to
+// beat" and a second parity oracle for the sweep; nothing in pyc2ray_b200/ links it.
+//
+// The declarations below are the reference's (src/asora/memory.cuh:3-16, src/asora/raytracing.cuh:22-35).
+#include "memory.cuh"
+#include "raytracing.cuh"
+
+#include <exception>
+#include <cstdio>
+
+extern "C" {
+
+int ref_device_init(int N, int num_src_par)
+{
+    try {
+        device_init(N, num_src_par);
+    } catch (const std::exception& e) {
+        fprintf(stderr, "ref_device_init: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
+void ref_device_close(void) { device_close(); }
+void ref_density_to_device(double* ndens, int N) { density_to_device(ndens, N); }
+void ref_photo_table_to_device(double* thin, double* thick, int NumTau) { photo_table_to_device(thin, thick, NumTau); }
+void ref_source_data_to_device(int* pos, double* flux, int NumSrc) { source_data_to_device(pos, flux, NumSrc); }
+int ref_do_all_sources(double R, double* coldensh_out, double sig, double dr, double* ndens, double* xh_av,
+                       double* phi_ion, int NumSrc, int m1, double minlogtau, double dlogtau, int NumTau)
+{
+    try {
+        do_all_sources_gpu(R, coldensh_out, sig, dr, ndens, xh_av, phi_ion, NumSrc, m1, minlogtau, dlogtau, NumTau);
+    } catch (const std::exception& e) {
+        fprintf(stderr, "ref_do_all_sources: %s\n", e.what());
+        return 1;
+    }
+    return (int)cudaGetLastError();
+}
+// device -> host copy of batch slot 0 of the reference's column-density scratch (memory.cu:20)
+int ref_copy_coldens(double* host, int N)
+{
+    return (int)cudaMemcpy(host, cdh_dev, sizeof(double) * (size_t)N * N * N, cudaMemcpyDeviceToHost);
+}
+}

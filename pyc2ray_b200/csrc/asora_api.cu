@@ -1,0 +1,454 @@
+// asora_api.cu -- the C ABI of libasora_b200.so (include/asora_b200.h): per-process device context,
+// host<->device staging, sweep-variant selection and launch.
+//
+// Replaces src/asora/memory.cu (device state, :20-129), the host driver do_all_sources_gpu
+// (src/asora/raytracing.cu:79-148) and the CPython wrappers (src/asora/python_module.cu).
+#include "../../include/asora_b200.h"
+#include "asora_common.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+namespace {
+
+struct Context {
+    bool init = false;
+    int N = 0;
+    int64_t ncell = 0;
+    int device = 0;
+    int sm_count = 0;
+    int smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double* buf[ASORA_BUF_COUNT] = {nullptr};
+    double* thin = nullptr;
+    double* thick = nullptr;
+    int ntab = 0;
+    int* src_pos = nullptr;
+    double* src_flux = nullptr;
+    int nsrc = 0;
+    SweepPlan plan;
+    // chemistry scratch
+    double* chem_partials = nullptr;
+    int* chem_iparts = nullptr;
+    int chem_blocks = 0;
+    // host-API chemistry staging (ncell doubles each), allocated on demand
+    double* chem_stage[6] = {nullptr};
+    int64_t chem_stage_n = 0;
+    // stats of the last sweep
+    int variant_forced = 0;
+    int last_variant = 0, last_launches = 0, last_qmax = 0, last_levels = 0;
+    int64_t last_updates = 0;
+    float last_ms = 0.f;
+};
+
+Context g;
+std::string g_err;
+
+int fail(const std::string& what)
+{
+    g_err = what;
+    return 1;
+}
+int fail_cuda(const char* where, cudaError_t e)
+{
+    g_err = std::string(where) + ": " + cudaGetErrorName(e) + " - " + cudaGetErrorString(e);
+    return 2;
+}
+#define CK(call)                                          \
+    do {                                                  \
+        cudaError_t _e = (call);                          \
+        if (_e != cudaSuccess) return fail_cuda(#call, _e); \
+    } while (0)
+
+int need_init()
+{
+    if (!g.init) return fail("GPU not initialized. Please initialize it by calling device_init(N)");
+    return 0;
+}
+
+int ensure_buffer(int which)
+{
+    if (which < 0 || which >= ASORA_BUF_COUNT) return fail("unknown buffer id");
+    if (!g.buf[which]) {
+        CK(cudaMalloc(&g.buf[which], sizeof(double) * g.ncell));
+        CK(cudaMemsetAsync(g.buf[which], 0, sizeof(double) * g.ncell, g.stream));
+    }
+    return 0;
+}
+
+int ensure_chem_scratch()
+{
+    if (!g.chem_partials) {
+        g.chem_blocks = chemistry_partial_blocks((int64_t)1 << 40);
+        CK(cudaMalloc(&g.chem_partials, sizeof(double) * (2 * g.chem_blocks + 2)));
+        CK(cudaMalloc(&g.chem_iparts, sizeof(int) * (g.chem_blocks + 1)));
+    }
+    return 0;
+}
+
+// Choose and launch the sweep for sources [begin, begin+count).  Inputs already on the device.
+int run_sweep(double R, double sig, double dr, int begin, int count, double minlogtau, double dlogtau,
+              int NumTau, bool zero_phi, double* coldens_grid)
+{
+    if (!g.thin || !g.thick) return fail("photo tables not on device: call photo_table_to_device first");
+    if (begin < 0 || count < 0 || begin + count > g.nsrc)
+        return fail("source range exceeds the list uploaded with source_data_to_device");
+    if (int rc = ensure_buffer(ASORA_BUF_NDENS)) return rc;
+    if (int rc = ensure_buffer(ASORA_BUF_XH_AV)) return rc;
+    if (int rc = ensure_buffer(ASORA_BUF_PHI_ION)) return rc;
+    const int N = g.N;
+    if (zero_phi) CK(cudaMemsetAsync(g.buf[ASORA_BUF_PHI_ION], 0, sizeof(double) * g.ncell, g.stream));
+
+    SweepParams p;
+    p.N = N;
+    p.q_max = asora_qmax(N, R);
+    p.last_r = N / 2 - 1 + (N % 2);
+    p.last_l = -N / 2;
+    p.R2 = R * R;
+    p.sig = sig;
+    p.dr = dr;
+    p.dr3 = dr * dr * dr;
+    p.volfac = ASORA_FOURPI * p.dr3;
+    p.minlogtau = minlogtau;
+    p.dlogtau = dlogtau;
+    p.NumTau = NumTau;
+    p.ntab = g.ntab;
+    p.ndens = g.buf[ASORA_BUF_NDENS];
+    p.xh_av = g.buf[ASORA_BUF_XH_AV];
+    p.phi_ion = g.buf[ASORA_BUF_PHI_ION];
+    p.thin = g.thin;
+    p.thick = g.thick;
+    p.src_pos = g.src_pos;
+    p.src_flux = g.src_flux;
+    p.src_begin = begin;
+    p.src_count = count;
+    p.coldens_out = coldens_grid;
+
+    g.last_qmax = p.q_max;
+    g.last_launches = 0;
+    g.last_updates = (int64_t)count * asora_count_cells(N, R);
+    g.last_ms = 0.f;
+
+    // Variant selection: the shared-memory sweep needs two levels of column densities per source.
+    int variant = g.variant_forced;
+    int S = 1, block = 256;
+    bool plan_ok = false;
+    if (variant != 2) {
+        const int lo_side = 2 * std::min(p.q_max, std::max(-p.last_l, p.last_r)) + 1;
+        if (p.q_max <= 127 && lo_side <= 255) {
+            if (!(g.plan.valid && g.plan.N == N && g.plan.R == R && g.plan.dr == dr)) {
+                std::string err;
+                if (!build_sweep_plan(g.plan, N, R, dr, err)) {
+                    if (variant == 1) return fail(err);
+                }
+            }
+            plan_ok = g.plan.valid;
+        }
+        if (plan_ok) {
+            const size_t per_src = sweep_smem_bytes(g.plan, 1);
+            const size_t budget = (size_t)g.smem_optin;
+            if (per_src > budget) {
+                plan_ok = false;
+            } else {
+                // sources per CTA: amortise the plan over S sources while keeping >= 2 CTAs per SM
+                S = 1;
+                if (count >= 4 * g.sm_count && 4 * per_src * 2 <= budget) S = 4;
+                else if (count >= 2 * g.sm_count && 2 * per_src * 2 <= budget) S = 2;
+                const int maxc = g.plan.max_level_cells;
+                block = maxc >= 4096 ? 1024 : (maxc >= 1024 ? 512 : 256);
+            }
+        }
+        if (variant == 1 && !plan_ok) return fail("sweep variant 1 forced but a level does not fit in shared memory");
+    }
+    if (variant == 0) variant = plan_ok ? 1 : 2;
+
+    CK(cudaEventRecord(g.ev0, g.stream));
+    if (variant == 1) {
+        g.last_levels = g.plan.nlevels;
+        cudaError_t e = launch_sweep_smem(g.plan, p, S, block, g.stream, &g.last_launches);
+        if (e != cudaSuccess) return fail_cuda("sweep_smem_kernel launch", e);
+    } else {
+        if (!p.coldens_out) {
+            if (int rc = ensure_buffer(ASORA_BUF_COLDENS)) return rc;
+            p.coldens_out = g.buf[ASORA_BUF_COLDENS];
+        }
+        cudaError_t e = launch_sweep_grid(p, g.stream, &g.last_launches, &g.last_levels);
+        if (e != cudaSuccess) return fail_cuda("sweep_grid_kernel launch", e);
+    }
+    CK(cudaEventRecord(g.ev1, g.stream));
+    g.last_variant = variant;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* asora_last_error(void) { return g_err.c_str(); }
+const char* asora_version(void) { return "asora_b200 0.1 (sm_100a)"; }
+
+int64_t asora_cells_per_source(int N, double R) { return asora_count_cells(N, R); }
+
+int asora_device_init(int N, int num_src_par)
+{
+    (void)num_src_par;
+    if (N <= 0 || N > 1600) return fail("device_init: mesh size out of range");
+    if (g.init) asora_device_close();
+    CK(cudaGetDevice(&g.device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, g.device));
+    if (prop.major < 10) return fail(std::string("device_init: ") + prop.name + " is not an sm_100 class GPU");
+    g.sm_count = prop.multiProcessorCount;
+    CK(cudaDeviceGetAttribute(&g.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, g.device));
+    g.N = N;
+    g.ncell = (int64_t)N * N * N;
+    CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&g.ev0));
+    CK(cudaEventCreate(&g.ev1));
+    g.init = true;
+    // the three grids the reference allocates up front (memory.cu:66-68)
+    if (int rc = ensure_buffer(ASORA_BUF_NDENS)) return rc;
+    if (int rc = ensure_buffer(ASORA_BUF_XH_AV)) return rc;
+    if (int rc = ensure_buffer(ASORA_BUF_PHI_ION)) return rc;
+    CK(cudaStreamSynchronize(g.stream));
+    printf("GPU Device %d: \"%s\" with compute capability %d.%d\n", g.device, prop.name, prop.major, prop.minor);
+    printf("Succesfully allocated %g Mb of device memory for grid of size N = %d (column densities stay on-chip)\n",
+           3.0 * g.ncell * sizeof(double) / 1e6, N);
+    fflush(stdout);
+    return 0;
+}
+
+int asora_device_close(void)
+{
+    if (!g.init) return 0;
+    cudaStreamSynchronize(g.stream);
+    for (int i = 0; i < ASORA_BUF_COUNT; i++) {
+        if (g.buf[i]) cudaFree(g.buf[i]);
+        g.buf[i] = nullptr;
+    }
+    if (g.thin) cudaFree(g.thin);
+    if (g.thick) cudaFree(g.thick);
+    if (g.src_pos) cudaFree(g.src_pos);
+    if (g.src_flux) cudaFree(g.src_flux);
+    if (g.chem_partials) cudaFree(g.chem_partials);
+    if (g.chem_iparts) cudaFree(g.chem_iparts);
+    for (int i = 0; i < 6; i++) {
+        if (g.chem_stage[i]) cudaFree(g.chem_stage[i]);
+        g.chem_stage[i] = nullptr;
+    }
+    g.chem_stage_n = 0;
+    g.thin = g.thick = nullptr;
+    g.src_pos = nullptr;
+    g.src_flux = nullptr;
+    g.chem_partials = nullptr;
+    g.chem_iparts = nullptr;
+    g.ntab = g.nsrc = 0;
+    free_sweep_plan(g.plan);
+    if (g.ev0) cudaEventDestroy(g.ev0);
+    if (g.ev1) cudaEventDestroy(g.ev1);
+    if (g.stream) cudaStreamDestroy(g.stream);
+    g.ev0 = g.ev1 = nullptr;
+    g.stream = nullptr;
+    g.init = false;
+    return 0;
+}
+
+int asora_density_to_device(const double* ndens, int N)
+{
+    if (int rc = need_init()) return rc;
+    if (N != g.N) return fail("density_to_device: N differs from device_init");
+    if (!ndens) return fail("density_to_device: null pointer");
+    return asora_buffer_upload(ASORA_BUF_NDENS, ndens);
+}
+
+int asora_photo_table_to_device(const double* thin_table, const double* thick_table, int NumTau)
+{
+    if (int rc = need_init()) return rc;
+    if (NumTau < 2 || !thin_table || !thick_table) return fail("photo_table_to_device: bad arguments");
+    if (g.thin) cudaFree(g.thin);
+    if (g.thick) cudaFree(g.thick);
+    g.thin = g.thick = nullptr;
+    CK(cudaMalloc(&g.thin, sizeof(double) * NumTau));
+    CK(cudaMalloc(&g.thick, sizeof(double) * NumTau));
+    CK(cudaMemcpyAsync(g.thin, thin_table, sizeof(double) * NumTau, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.thick, thick_table, sizeof(double) * NumTau, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    g.ntab = NumTau;
+    return 0;
+}
+
+int asora_source_data_to_device(const int32_t* pos, const double* flux, int NumSrc)
+{
+    if (int rc = need_init()) return rc;
+    if (NumSrc < 0 || (NumSrc > 0 && (!pos || !flux))) return fail("source_data_to_device: bad arguments");
+    if (g.src_pos) cudaFree(g.src_pos);
+    if (g.src_flux) cudaFree(g.src_flux);
+    g.src_pos = nullptr;
+    g.src_flux = nullptr;
+    g.nsrc = 0;
+    if (NumSrc == 0) return 0;
+    // The sweep is periodic (modulo_gpu, raytracing.cu:270-272): reduce positions to [0,N) once here.
+    std::vector<int32_t> wrapped(3 * (size_t)NumSrc);
+    for (size_t t = 0; t < wrapped.size(); t++) wrapped[t] = ((pos[t] % g.N) + g.N) % g.N;
+    CK(cudaMalloc(&g.src_pos, sizeof(int32_t) * 3 * (size_t)NumSrc));
+    CK(cudaMalloc(&g.src_flux, sizeof(double) * (size_t)NumSrc));
+    CK(cudaMemcpyAsync(g.src_pos, wrapped.data(), sizeof(int32_t) * 3 * (size_t)NumSrc, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.src_flux, flux, sizeof(double) * (size_t)NumSrc, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    g.nsrc = NumSrc;
+    return 0;
+}
+
+int asora_do_all_sources(double R, double sig, double dr, const double* xh_av, double* phi_ion, int NumSrc,
+                         int N, double minlogtau, double dlogtau, int NumTau)
+{
+    if (int rc = need_init()) return rc;
+    if (N != g.N) return fail("do_all_sources: m1 differs from device_init");
+    if (!xh_av || !phi_ion) return fail("do_all_sources: null pointer");
+    CK(cudaMemcpyAsync(g.buf[ASORA_BUF_XH_AV], xh_av, sizeof(double) * g.ncell, cudaMemcpyHostToDevice, g.stream));
+    if (int rc = run_sweep(R, sig, dr, 0, NumSrc, minlogtau, dlogtau, NumTau, true, nullptr)) return rc;
+    CK(cudaMemcpyAsync(phi_ion, g.buf[ASORA_BUF_PHI_ION], sizeof(double) * g.ncell, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1);
+    return 0;
+}
+
+int asora_debug_single_source(double R, double sig, double dr, const double* xh_av, int src_index,
+                              double minlogtau, double dlogtau, int NumTau, double* coldensh_out, double* phi_ion)
+{
+    if (int rc = need_init()) return rc;
+    if (!xh_av || !coldensh_out) return fail("debug_single_source: null pointer");
+    if (int rc = ensure_buffer(ASORA_BUF_COLDENS)) return rc;
+    CK(cudaMemcpyAsync(g.buf[ASORA_BUF_XH_AV], xh_av, sizeof(double) * g.ncell, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemsetAsync(g.buf[ASORA_BUF_COLDENS], 0, sizeof(double) * g.ncell, g.stream));
+    if (int rc = run_sweep(R, sig, dr, src_index, 1, minlogtau, dlogtau, NumTau, true, g.buf[ASORA_BUF_COLDENS]))
+        return rc;
+    CK(cudaMemcpyAsync(coldensh_out, g.buf[ASORA_BUF_COLDENS], sizeof(double) * g.ncell, cudaMemcpyDeviceToHost, g.stream));
+    if (phi_ion)
+        CK(cudaMemcpyAsync(phi_ion, g.buf[ASORA_BUF_PHI_ION], sizeof(double) * g.ncell, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1);
+    return 0;
+}
+
+int asora_raytrace_device(double R, double sig, double dr, int src_begin, int src_count, double minlogtau,
+                          double dlogtau, int NumTau, int zero_phi)
+{
+    if (int rc = need_init()) return rc;
+    return run_sweep(R, sig, dr, src_begin, src_count, minlogtau, dlogtau, NumTau, zero_phi != 0, nullptr);
+}
+
+int asora_sync(void)
+{
+    if (int rc = need_init()) return rc;
+    CK(cudaStreamSynchronize(g.stream));
+    if (g.last_launches > 0) cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1);
+    return 0;
+}
+
+void* asora_device_buffer(int which)
+{
+    if (need_init()) return nullptr;
+    if (ensure_buffer(which)) return nullptr;
+    cudaStreamSynchronize(g.stream);
+    return g.buf[which];
+}
+
+int asora_buffer_upload(int which, const double* host)
+{
+    if (int rc = need_init()) return rc;
+    if (int rc = ensure_buffer(which)) return rc;
+    CK(cudaMemcpyAsync(g.buf[which], host, sizeof(double) * g.ncell, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+int asora_buffer_download(int which, double* host)
+{
+    if (int rc = need_init()) return rc;
+    if (int rc = ensure_buffer(which)) return rc;
+    CK(cudaMemcpyAsync(host, g.buf[which], sizeof(double) * g.ncell, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+int asora_global_pass_device(double dt, double bh00, double albpow, double colh0, double temph0, double abu_c,
+                             int* conv_flag, double* sum_xh1, double* sum_xh0)
+{
+    if (int rc = need_init()) return rc;
+    const int ids[] = {ASORA_BUF_NDENS, ASORA_BUF_TEMP, ASORA_BUF_XH, ASORA_BUF_XH_AV, ASORA_BUF_XH_INTERMED,
+                       ASORA_BUF_PHI_ION};
+    for (int id : ids)
+        if (int rc = ensure_buffer(id)) return rc;
+    if (int rc = ensure_chem_scratch()) return rc;
+    cudaError_t e = launch_global_pass(dt, g.buf[ASORA_BUF_NDENS], g.buf[ASORA_BUF_TEMP], g.buf[ASORA_BUF_XH],
+                                       g.buf[ASORA_BUF_XH_AV], g.buf[ASORA_BUF_XH_INTERMED], g.buf[ASORA_BUF_PHI_ION],
+                                       bh00, albpow, colh0, temph0, abu_c, g.ncell, 1, g.chem_partials,
+                                       g.chem_iparts, g.chem_blocks, conv_flag, sum_xh1, sum_xh0, g.stream);
+    if (e != cudaSuccess) return fail_cuda("global_pass_kernel", e);
+    return 0;
+}
+
+// Host-buffer chemistry.  Works without device_init (hydrogenODE is usable stand-alone:
+// pyc2ray/chemistry.py:43-97), on whatever device is current.
+int asora_global_pass(double dt, const double* ndens, const double* temp, const double* xh, double* xh_av,
+                      double* xh_intermed, const double* phi_ion, double bh00, double albpow, double colh0,
+                      double temph0, double abu_c, int64_t ncell, int* conv_flag)
+{
+    if (ncell <= 0) return fail("global_pass: ncell must be positive");
+    if (!ndens || !temp || !xh || !xh_av || !xh_intermed || !phi_ion) return fail("global_pass: null pointer");
+    cudaStream_t st = g.init ? g.stream : (cudaStream_t)0;
+    if (g.chem_stage_n < ncell) {
+        for (int i = 0; i < 6; i++) {
+            if (g.chem_stage[i]) cudaFree(g.chem_stage[i]);
+            g.chem_stage[i] = nullptr;
+        }
+        g.chem_stage_n = 0;
+        for (int i = 0; i < 6; i++) CK(cudaMalloc(&g.chem_stage[i], sizeof(double) * ncell));
+        g.chem_stage_n = ncell;
+    }
+    if (int rc = ensure_chem_scratch()) return rc;
+    const double* src[6] = {ndens, temp, xh, xh_av, xh_intermed, phi_ion};
+    const size_t bytes = sizeof(double) * (size_t)ncell;
+    // aliased host arrays share one device copy so the kernel sees the same aliasing
+    double* dev[6];
+    for (int i = 0; i < 6; i++) {
+        dev[i] = g.chem_stage[i];
+        for (int j = 0; j < i; j++)
+            if (src[j] == src[i]) dev[i] = dev[j];
+        if (dev[i] == g.chem_stage[i]) CK(cudaMemcpyAsync(dev[i], src[i], bytes, cudaMemcpyHostToDevice, st));
+    }
+    int flag = 0;
+    cudaError_t e = launch_global_pass(dt, dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], bh00, albpow, colh0,
+                                       temph0, abu_c, ncell, 1, g.chem_partials, g.chem_iparts, g.chem_blocks,
+                                       &flag, nullptr, nullptr, st);
+    if (e != cudaSuccess) return fail_cuda("global_pass_kernel", e);
+    // chemistry.f90:107-108 write-back; xh_av first, xh_intermed last (see chemistry.cu)
+    CK(cudaMemcpyAsync(xh_av, dev[3], bytes, cudaMemcpyDeviceToHost, st));
+    if (xh_intermed != xh_av) CK(cudaMemcpyAsync(xh_intermed, dev[4], bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (conv_flag) *conv_flag = flag;
+    return 0;
+}
+
+int asora_set_sweep_variant(int variant)
+{
+    if (variant < 0 || variant > 2) return fail("set_sweep_variant: unknown variant");
+    g.variant_forced = variant;
+    return 0;
+}
+
+int asora_last_sweep_stats(int* variant, int* launches, int64_t* updates, int* q_max, int* levels, float* kernel_ms)
+{
+    if (variant) *variant = g.last_variant;
+    if (launches) *launches = g.last_launches;
+    if (updates) *updates = g.last_updates;
+    if (q_max) *q_max = g.last_qmax;
+    if (levels) *levels = g.last_levels;
+    if (kernel_ms) *kernel_ms = g.last_ms;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,101 @@
+// asora_common.cuh -- shared declarations of libasora_b200 (sm_100a).
+//
+// Vocabulary (follows the reference, phirling/pyc2ray):
+//   source      a point emitter at a mesh cell, flux in units of 1e48 photons/s
+//   sweep       the short-characteristics pass that propagates HI column density outwards from a
+//               source and turns (column in, column out) into a photo-ionisation rate per cell
+//   level       all cells at one Chebyshev distance m = max(|di|,|dj|,|dk|) from the source.  Every
+//               non-zero interpolation weight of a level-m cell points at a level-(m-1) cell, so a
+//               level is the widest set of cells that can be updated concurrently, and a sweep
+//               needs min(q_max, N/2)+1 dependent steps instead of the q_max+1 octahedral shells
+//               of src/asora/raytracing.cu:198 (proof: DESIGN.md, "Chebyshev levels")
+//   plan        the source-independent description of a sweep (cell offsets, interpolation
+//               fractions, path lengths, upstream slots), built once per (N, R, dr) on the host and
+//               shared by all sources through L2
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#define ASORA_FOURPI 12.566370614359172463991853874177  // src/asora/raytracing.cu:12
+#define ASORA_SQRT3 1.73205080757                       // raytracing.cu:14,435
+#define ASORA_SQRT2 1.41421356237                       // raytracing.cu:439
+#define ASORA_MAX_COLDENSH 2e30                         // raytracing.cu:15
+#define ASORA_TAU_PHOTO_LIMIT 1.0e-7                    // src/asora/rates.cu:7
+
+// Plan cell flags
+#define PC_RATED 1u   // inside the R_max sphere: dist2/(dr*dr) <= R*R  (raytracing.cu:315)
+#define PC_SOURCE 2u  // the source cell itself (raytracing.cu:285-294)
+#define PC_DIAG2 4u   // incoming column scaled by sqrt(2) (raytracing.cu:431-441)
+#define PC_DIAG3 8u   // incoming column scaled by sqrt(3)
+
+// One cell of the sweep plan (48 bytes, three 16-byte loads).
+struct __align__(16) PlanCell {
+    double wA, wB;   // |minor offset| / |dominant offset| for the two minor axes
+    double path;     // path length through the cell in cell units (raytracing.cu:444,489,533)
+    double np;       // (di^2+dj^2+dk^2) * path ; vol_ph = 4 pi dr^3 * np (raytracing.cu:300-307)
+    uint16_t nb[4];  // slots, in the previous level, of the 4 upstream cells c1..c4
+    int8_t d[3];     // offset from the source
+    uint8_t flags;
+    uint32_t pad;
+};
+static_assert(sizeof(PlanCell) == 48, "PlanCell must be 48 bytes");
+
+struct SweepPlan {
+    int N = 0;
+    double R = 0, dr = 0;
+    int q_max = 0;
+    int nlevels = 0;
+    int max_level_cells = 0;
+    int64_t ncells = 0;                // cells per source
+    std::vector<int> level_start;      // nlevels+1
+    std::vector<PlanCell> cells;       // level-major, lexicographic (di,dj,dk) inside a level
+    PlanCell* d_cells = nullptr;
+    int* d_level_start = nullptr;
+    bool valid = false;
+};
+
+// Scalars every sweep kernel needs.
+struct SweepParams {
+    int N;
+    int q_max;
+    int last_l, last_r;       // raytracing.cu:122-123
+    double R2;                // R*R
+    double sig, dr;
+    double dr3;               // dr*dr*dr (source-cell volume, raytracing.cu:292)
+    double volfac;            // 4 pi dr^3
+    double minlogtau, dlogtau;
+    int NumTau;               // index clamp as passed by the caller (rates.cu:78-79)
+    int ntab;                 // uploaded table length
+    const double* ndens;
+    const double* xh_av;
+    double* phi_ion;
+    const double* thin;
+    const double* thick;
+    const int* src_pos;
+    const double* src_flux;
+    int src_begin, src_count;
+    double* coldens_out;      // optional N^3 grid receiving outgoing column densities (debug) or
+                              // the L2-resident scratch of the grid-cooperative variant
+};
+
+// host-side helpers implemented in sweep_plan.cu
+int asora_qmax(int N, double R);
+int64_t asora_count_cells(int N, double R);
+bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, std::string& err);
+void free_sweep_plan(SweepPlan& plan);
+
+// launchers implemented in sweep_kernels.cu
+size_t sweep_smem_bytes(const SweepPlan& plan, int sources_per_cta);
+cudaError_t launch_sweep_smem(const SweepPlan& plan, const SweepParams& p, int sources_per_cta, int block,
+                              cudaStream_t stream, int* launches);
+cudaError_t launch_sweep_grid(const SweepParams& p, cudaStream_t stream, int* launches, int* levels);
+
+// chemistry.cu
+cudaError_t launch_global_pass(double dt, const double* ndens, const double* temp, const double* xh,
+                               double* xh_av, double* xh_intermed, const double* phi_ion, double bh00,
+                               double albpow, double colh0, double temph0, double abu_c, int64_t ncell,
+                               int store_av_first, double* d_partials, int* d_iparts, int nblocks_max,
+                               int* conv_flag, double* sum1, double* sum0, cudaStream_t stream);
+int chemistry_partial_blocks(int64_t ncell);

@@ -1,0 +1,331 @@
+// sweep_kernels.cu -- the ASORA sweep for sm_100a: column-density propagation by Chebyshev levels,
+// photo-ionisation table lookup and rate accumulation.
+//
+// Replaces evolve0D_gpu + cinterp_gpu (src/asora/raytracing.cu:155-535) and photoion_rates_gpu +
+// photo_lookuptable (src/asora/rates.cu:16-83).  Two variants share the per-cell arithmetic:
+//
+//   sweep_smem_kernel<S>  one CTA sweeps S sources at once.  The outgoing column densities of the
+//                         previous and the current level live in shared memory (2 x S x max level
+//                         cells doubles); nothing per-source is ever written to HBM.  All geometry
+//                         comes from the plan (sweep_plan.cu), amortised over the S sources.
+//   sweep_grid_kernel     cooperative launch, the whole GPU sweeps one source at a time, one
+//                         grid-wide barrier per level; column densities go through an N^3 scratch
+//                         grid that stays in the 126 MB L2.  Geometry is computed on the fly.  Used
+//                         when a level does not fit in shared memory (large radii / full box).
+#include "asora_common.cuh"
+
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+// ---------------------------------------------------------------------------------------------------
+// per-cell arithmetic
+// ---------------------------------------------------------------------------------------------------
+
+// rates.cu:70-83.  `ntab` additionally clamps to the uploaded table length (reference bug N6: the
+// Python callers pass NumTau = table length, which lets i1 reach one element past the table).
+__device__ __forceinline__ double photo_lookuptable(const double* __restrict__ table, double tau,
+                                                    double minlogtau, double dlogtau, int NumTau, int ntab)
+{
+    double logtau = log10(fmax(1.0e-20, tau));
+    double real_i = fmin((double)NumTau, fmax(0.0, 1.0 + (logtau - minlogtau) / dlogtau));
+    int i0 = (int)real_i;
+    int i1 = min(NumTau, i0 + 1);
+    double residual = real_i - (double)i0;
+    i0 = min(i0, ntab - 1);
+    i1 = min(i1, ntab - 1);
+    double t0 = __ldg(table + i0), t1 = __ldg(table + i1);
+    return t0 + residual * (t1 - t0);
+}
+
+// rates.cu:16-41
+__device__ __forceinline__ double photoion_rate(double strength, double coldens_in, double coldens_out,
+                                                double Vfact, const SweepParams& p)
+{
+    double tau_in = coldens_in * p.sig;
+    double tau_out = coldens_out * p.sig;
+    double prefact = strength / Vfact;
+    double phi_photo_in = prefact * photo_lookuptable(p.thick, tau_in, p.minlogtau, p.dlogtau, p.NumTau, p.ntab);
+    if (fabs(tau_out - tau_in) > ASORA_TAU_PHOTO_LIMIT) {
+        double phi_photo_out =
+            prefact * photo_lookuptable(p.thick, tau_out, p.minlogtau, p.dlogtau, p.NumTau, p.ntab);
+        return phi_photo_in - phi_photo_out;
+    }
+    return prefact * (tau_out - tau_in) *
+           photo_lookuptable(p.thin, tau_out, p.minlogtau, p.dlogtau, p.NumTau, p.ntab);
+}
+
+// raytracing.cu:33
+__device__ __forceinline__ double weightf(double cd, double sig) { return 1.0 / fmax(0.6, cd * sig); }
+
+// raytracing.cu:405-441 with s1..s4 written in terms of the minor-axis fractions (sweep_plan.cu).
+// Corners whose bilinear weight is exactly zero are never allowed to contribute (the reference
+// multiplies whatever it reads by 0: raytracing.cu:416-428, SURVEY note N3).
+__device__ __forceinline__ double interp_coldens(double c1, double c2, double c3, double c4, double wA,
+                                                 double wB, double sig, unsigned flags)
+{
+    const double uA = 1.0 - wA, uB = 1.0 - wB;
+    const double s1 = wA * wB, s2 = wB * uA, s3 = wA * uB, s4 = uA * uB;
+    c1 = (s1 != 0.0) ? c1 : 0.0;
+    c2 = (s2 != 0.0) ? c2 : 0.0;
+    c3 = (s3 != 0.0) ? c3 : 0.0;
+    c4 = (s4 != 0.0) ? c4 : 0.0;
+    const double w1 = s1 * weightf(c1, sig);
+    const double w2 = s2 * weightf(c2, sig);
+    const double w3 = s3 * weightf(c3, sig);
+    const double w4 = s4 * weightf(c4, sig);
+    double cdensi = (c1 * w1 + c2 * w2 + c3 * w3 + c4 * w4) / (w1 + w2 + w3 + w4);
+    if (flags & PC_DIAG3) cdensi = ASORA_SQRT3 * cdensi;
+    if (flags & PC_DIAG2) cdensi = ASORA_SQRT2 * cdensi;
+    return cdensi;
+}
+
+__device__ __forceinline__ int wrap(int i, int N)
+{
+    i += (i < 0) ? N : 0;
+    i -= (i >= N) ? N : 0;
+    return i;
+}
+
+// Everything after the incoming column density is known: raytracing.cu:300-329.
+// Returns the outgoing column density.
+__device__ __forceinline__ double finish_cell(double coldensh_in, double path_cells, double np, unsigned flags,
+                                              double nHI_p, double strength, size_t pos, const SweepParams& p)
+{
+    double path, vol_ph;
+    if (flags & PC_SOURCE) {
+        path = 0.5 * p.dr;
+        vol_ph = p.dr3;
+    } else {
+        path = path_cells * p.dr;
+        vol_ph = np * p.volfac;
+    }
+    const double cdho = coldensh_in + nHI_p * path;
+    if ((flags & PC_RATED) && coldensh_in <= ASORA_MAX_COLDENSH) {
+        double phi = photoion_rate(strength, coldensh_in, cdho, vol_ph, p);
+        phi /= nHI_p;
+        // one fire-and-forget fp64 reduction per rated (source, cell) pair: RED.E.ADD.F64 at L2
+        atomicAdd(p.phi_ion + pos, phi);
+    }
+    return cdho;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// variant 1: shared-memory level sweep, S sources per CTA
+// ---------------------------------------------------------------------------------------------------
+template <int S>
+__global__ void sweep_smem_kernel(const PlanCell* __restrict__ plan, const int* __restrict__ level_start,
+                                  int nlevels, int max_level_cells, SweepParams p)
+{
+    extern __shared__ double sh_cd[];  // [2][S][max_level_cells]
+    const int N = p.N;
+    const int first = blockIdx.x * S;
+
+    int i0[S], j0[S], k0[S];
+    double flux[S];
+    bool live[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        live[s] = (first + s) < p.src_count;
+        const int ns = p.src_begin + (live[s] ? first + s : 0);
+        i0[s] = p.src_pos[3 * ns + 0];
+        j0[s] = p.src_pos[3 * ns + 1];
+        k0[s] = p.src_pos[3 * ns + 2];
+        flux[s] = p.src_flux[ns];
+    }
+
+    for (int m = 0; m < nlevels; m++) {
+        const int beg = __ldg(level_start + m), end = __ldg(level_start + m + 1);
+        double* cur = sh_cd + (size_t)(m & 1) * S * max_level_cells;
+        const double* prev = sh_cd + (size_t)((m & 1) ^ 1) * S * max_level_cells;
+        for (int e = beg + threadIdx.x; e < end; e += blockDim.x) {
+            // plan cell: three 16-byte read-only loads, shared by the S sources
+            const int4* q = reinterpret_cast<const int4*>(plan + e);
+            const int4 r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2);
+            const double wA = __hiloint2double(r0.y, r0.x), wB = __hiloint2double(r0.w, r0.z);
+            const double path = __hiloint2double(r1.y, r1.x), np = __hiloint2double(r1.w, r1.z);
+            const int nb1 = r2.x & 0xffff, nb2 = (unsigned)r2.x >> 16;
+            const int nb3 = r2.y & 0xffff, nb4 = (unsigned)r2.y >> 16;
+            const int di = (int)(signed char)(r2.z & 0xff), dj = (int)(signed char)((r2.z >> 8) & 0xff);
+            const int dk = (int)(signed char)((r2.z >> 16) & 0xff);
+            const unsigned flags = ((unsigned)r2.z >> 24) & 0xffu;
+            const int slot = e - beg;
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                if (!live[s]) continue;
+                const int i = wrap(i0[s] + di, N), j = wrap(j0[s] + dj, N), k = wrap(k0[s] + dk, N);
+                const size_t pos = ((size_t)i * N + j) * N + k;
+                const double xh_av_p = __ldg(p.xh_av + pos);
+                const double nHI_p = __ldg(p.ndens + pos) * (1.0 - xh_av_p);
+                double cin = 0.0;
+                if (!(flags & PC_SOURCE)) {
+                    const double* pv = prev + s * max_level_cells;
+                    cin = interp_coldens(pv[nb1], pv[nb2], pv[nb3], pv[nb4], wA, wB, p.sig, flags);
+                }
+                const double cdho = finish_cell(cin, path, np, flags, nHI_p, flux[s], pos, p);
+                cur[s * max_level_cells + slot] = cdho;
+                if (p.coldens_out) p.coldens_out[pos] = cdho;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+size_t sweep_smem_bytes(const SweepPlan& plan, int S)
+{
+    return (size_t)2 * S * plan.max_level_cells * sizeof(double);
+}
+
+template <int S>
+static cudaError_t launch_smem_t(const SweepPlan& plan, const SweepParams& p, int block, cudaStream_t stream)
+{
+    const size_t smem = sweep_smem_bytes(plan, S);
+    cudaError_t e = cudaFuncSetAttribute(sweep_smem_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int grid = (p.src_count + S - 1) / S;
+    sweep_smem_kernel<S><<<grid, block, smem, stream>>>(plan.d_cells, plan.d_level_start, plan.nlevels,
+                                                        plan.max_level_cells, p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sweep_smem(const SweepPlan& plan, const SweepParams& p, int S, int block, cudaStream_t stream,
+                              int* launches)
+{
+    if (p.src_count <= 0) return cudaSuccess;
+    if (launches) *launches += 1;
+    switch (S) {
+        case 1: return launch_smem_t<1>(plan, p, block, stream);
+        case 2: return launch_smem_t<2>(plan, p, block, stream);
+        case 4: return launch_smem_t<4>(plan, p, block, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// variant 2: grid-cooperative level sweep, whole GPU per source
+// ---------------------------------------------------------------------------------------------------
+
+// Enumerate the cube shell max(|di|,|dj|,|dk|) == m, k fastest on the x and y faces.
+__device__ __forceinline__ void shell_cell(long long t, int m, int& di, int& dj, int& dk)
+{
+    const long long w = 2 * m + 1, v = 2 * m - 1;
+    const long long fx = w * w, fy = v * w, fz = v * v;
+    if (t < 2 * fx) {
+        const int sgn = (t < fx) ? 1 : -1;
+        if (t >= fx) t -= fx;
+        di = sgn * m;
+        dj = (int)(t / w) - m;
+        dk = (int)(t % w) - m;
+    } else if (t < 2 * fx + 2 * fy) {
+        t -= 2 * fx;
+        const int sgn = (t < fy) ? 1 : -1;
+        if (t >= fy) t -= fy;
+        dj = sgn * m;
+        di = (int)(t / w) - (m - 1);
+        dk = (int)(t % w) - m;
+    } else {
+        t -= 2 * fx + 2 * fy;
+        const int sgn = (t < fz) ? 1 : -1;
+        if (t >= fz) t -= fz;
+        dk = sgn * m;
+        di = (int)(t / v) - (m - 1);
+        dj = (int)(t % v) - (m - 1);
+    }
+}
+
+__device__ __forceinline__ int isign1(int x) { return x >= 0 ? 1 : -1; }
+
+__global__ void sweep_grid_kernel(SweepParams p, int nlevels)
+{
+    cg::grid_group grid = cg::this_grid();
+    const int N = p.N;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double* __restrict__ slab = p.coldens_out;
+
+    for (int sidx = 0; sidx < p.src_count; sidx++) {
+        const int ns = p.src_begin + sidx;
+        const int i0 = p.src_pos[3 * ns + 0], j0 = p.src_pos[3 * ns + 1], k0 = p.src_pos[3 * ns + 2];
+        const double strength = p.src_flux[ns];
+        for (int m = 0; m < nlevels; m++) {
+            const long long ncell = (m == 0) ? 1 : 24LL * m * m + 2;
+            for (long long t = tid; t < ncell; t += nthreads) {
+                int di = 0, dj = 0, dk = 0;
+                if (m > 0) shell_cell(t, m, di, dj, dk);
+                const int ia = abs(di), ja = abs(dj), ka = abs(dk);
+                if (ia + ja + ka > p.q_max) continue;
+                if (di < p.last_l || di > p.last_r || dj < p.last_l || dj > p.last_r || dk < p.last_l ||
+                    dk > p.last_r)
+                    continue;
+                const int i = wrap(i0 + di, N), j = wrap(j0 + dj, N), k = wrap(k0 + dk, N);
+                const size_t pos = ((size_t)i * N + j) * N + k;
+                const double xh_av_p = __ldg(p.xh_av + pos);
+                const double nHI_p = __ldg(p.ndens + pos) * (1.0 - xh_av_p);
+                unsigned flags = 0;
+                double cin = 0.0, path = 0.5, np = 0.0;
+                if (m == 0) {
+                    flags = PC_SOURCE | PC_RATED;
+                } else {
+                    // upstream cell coordinates (periodic): one step towards the source on each axis
+                    const int im = wrap(i - isign1(di), N), jm = wrap(j - isign1(dj), N),
+                              km = wrap(k - isign1(dk), N);
+                    int a, b, c;
+                    size_t q1, q2, q3, q4;
+                    const size_t NN = (size_t)N * N;
+                    if (ka >= ja && ka >= ia) {  // raytracing.cu:394
+                        a = ia; b = ja; c = ka;
+                        q1 = im * NN + (size_t)jm * N + km; q2 = i * NN + (size_t)jm * N + km;
+                        q3 = im * NN + (size_t)j * N + km;  q4 = i * NN + (size_t)j * N + km;
+                    } else if (ja >= ia && ja >= ka) {  // raytracing.cu:446
+                        a = ia; b = ka; c = ja;
+                        q1 = im * NN + (size_t)jm * N + km; q2 = i * NN + (size_t)jm * N + km;
+                        q3 = im * NN + (size_t)jm * N + k;  q4 = i * NN + (size_t)jm * N + k;
+                    } else {  // raytracing.cu:491
+                        a = ja; b = ka; c = ia;
+                        q1 = im * NN + (size_t)jm * N + km; q2 = im * NN + (size_t)j * N + km;
+                        q3 = im * NN + (size_t)jm * N + k;  q4 = im * NN + (size_t)j * N + k;
+                    }
+                    const double dc = (double)c, da = (double)a, db = (double)b;
+                    const double wA = da / dc, wB = db / dc;
+                    path = sqrt((da * da + db * db) / (dc * dc) + 1.0);
+                    np = (double)(ia * ia + ja * ja + ka * ka) * path;
+                    if (c == 1 && (a == 1 || b == 1)) flags |= (a == 1 && b == 1) ? PC_DIAG3 : PC_DIAG2;
+                    // sphere test in the reference's own form (raytracing.cu:302-305,315)
+                    const double xs = p.dr * (double)di, ys = p.dr * (double)dj, zs = p.dr * (double)dk;
+                    const double dist2 = __fma_rn(zs, zs, __fma_rn(ys, ys, __dmul_rn(xs, xs)));
+                    if (dist2 / (p.dr * p.dr) <= p.R2) flags |= PC_RATED;
+                    // the scratch grid is written by other SMs: read it at L2 (ld.global.cg), and skip
+                    // zero-weight corners, which may never have been written for this source
+                    const double c1 = (wA * wB != 0.0) ? __ldcg(slab + q1) : 0.0;
+                    const double c2 = (wB * (1.0 - wA) != 0.0) ? __ldcg(slab + q2) : 0.0;
+                    const double c3 = (wA * (1.0 - wB) != 0.0) ? __ldcg(slab + q3) : 0.0;
+                    const double c4 = ((1.0 - wA) * (1.0 - wB) != 0.0) ? __ldcg(slab + q4) : 0.0;
+                    cin = interp_coldens(c1, c2, c3, c4, wA, wB, p.sig, flags);
+                }
+                const double cdho = finish_cell(cin, path, np, flags, nHI_p, strength, pos, p);
+                __stcg(slab + pos, cdho);
+            }
+            grid.sync();
+        }
+    }
+}
+
+cudaError_t launch_sweep_grid(const SweepParams& p, cudaStream_t stream, int* launches, int* levels)
+{
+    if (p.src_count <= 0) return cudaSuccess;
+    int dev = 0, sms = 0, per_sm = 0;
+    const int block = 512;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_grid_kernel, block, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    // levels 0..min(q_max, max(|last_l|, last_r))
+    int nlevels = min(p.q_max, max(-p.last_l, p.last_r)) + 1;
+    if (levels) *levels = nlevels;
+    SweepParams pc = p;
+    void* args[] = {(void*)&pc, (void*)&nlevels};
+    if (launches) *launches += 1;
+    return cudaLaunchCooperativeKernel((void*)sweep_grid_kernel, dim3(sms * per_sm), dim3(block), args, 0, stream);
+}

@@ -1,0 +1,206 @@
+// sweep_plan.cu -- host-side construction of the source-independent sweep plan.
+//
+// The geometry of the short-characteristics interpolation depends only on the offset of a cell from
+// its source (src/asora/raytracing.cu:370-386,397-408,444), so it is tabulated once per (N, R, dr)
+// and shared by every source: the sweep kernel then does no index arithmetic beyond the periodic
+// wrap of one cell.  Cells are grouped in Chebyshev levels (see asora_common.cuh) and ordered
+// lexicographically in (di,dj,dk) inside a level, so that consecutive threads touch consecutive k
+// (the contiguous axis of the grids, raytracing.cu:30) on four of the six faces of a level, and so
+// that the upstream slots of consecutive cells are consecutive shared-memory words.
+#include "asora_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+// raytracing.cu:101  (SQRT3 is the 12-digit literal of raytracing.cu:14)
+int asora_qmax(int N, double R)
+{
+    return (int)std::ceil(ASORA_SQRT3 * std::min(R, ASORA_SQRT3 * N / 2.0));
+}
+
+static inline void clip_bounds(int N, int& last_l, int& last_r)
+{
+    last_r = N / 2 - 1 + (N % 2);  // raytracing.cu:122
+    last_l = -N / 2;               // raytracing.cu:123
+}
+
+// |octahedron(q_max) & cube|  (raytracing.cu:202,241)
+int64_t asora_count_cells(int N, double R)
+{
+    const int q = asora_qmax(N, R);
+    int ll, lr;
+    clip_bounds(N, ll, lr);
+    int64_t cnt = 0;
+    for (int i = ll; i <= lr; i++)
+        for (int j = ll; j <= lr; j++) {
+            int rem = q - std::abs(i) - std::abs(j);
+            if (rem < 0) continue;
+            int lo = std::max(-rem, ll), hi = std::min(rem, lr);
+            cnt += hi - lo + 1;
+        }
+    return cnt;
+}
+
+static inline int sign1(int x) { return x >= 0 ? 1 : -1; }  // raytracing.cu:27
+
+bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, std::string& err)
+{
+    free_sweep_plan(plan);
+    const int Q = asora_qmax(N, R);
+    int ll, lr;
+    clip_bounds(N, ll, lr);
+    const int lo = std::max(ll, -Q), hi = std::min(lr, Q);
+    const int side = hi - lo + 1;
+    if (Q > 127 || side > 255) {
+        err = "sweep plan: radius too large for the shared-memory variant";
+        return false;
+    }
+    const int nlevels = std::max(-lo, hi) + 1;
+    // pass 1: level sizes
+    std::vector<int> count(nlevels, 0);
+    for (int i = lo; i <= hi; i++)
+        for (int j = lo; j <= hi; j++)
+            for (int k = lo; k <= hi; k++) {
+                if (std::abs(i) + std::abs(j) + std::abs(k) > Q) continue;
+                count[std::max(std::abs(i), std::max(std::abs(j), std::abs(k)))]++;
+            }
+    plan.level_start.assign(nlevels + 1, 0);
+    int maxc = 0;
+    for (int m = 0; m < nlevels; m++) {
+        plan.level_start[m + 1] = plan.level_start[m] + count[m];
+        maxc = std::max(maxc, count[m]);
+    }
+    // drop empty trailing levels (cannot happen: the octahedron tips reach every level up to min(Q, bound))
+    if (maxc > 65535) {
+        err = "sweep plan: level too large for 16-bit slots";
+        return false;
+    }
+    const int64_t total = plan.level_start[nlevels];
+    plan.cells.resize(total);
+    // pass 2: slots (rank inside the level, lexicographic enumeration order)
+    std::vector<int32_t> slot((size_t)side * side * side, -1);
+    std::vector<int> fill(nlevels, 0);
+    auto sidx = [&](int i, int j, int k) { return ((size_t)(i - lo) * side + (j - lo)) * side + (k - lo); };
+    for (int i = lo; i <= hi; i++)
+        for (int j = lo; j <= hi; j++)
+            for (int k = lo; k <= hi; k++) {
+                if (std::abs(i) + std::abs(j) + std::abs(k) > Q) continue;
+                int m = std::max(std::abs(i), std::max(std::abs(j), std::abs(k)));
+                slot[sidx(i, j, k)] = fill[m]++;
+            }
+    // pass 3: geometry
+    const double R2 = R * R;
+    for (int i = lo; i <= hi; i++)
+        for (int j = lo; j <= hi; j++)
+            for (int k = lo; k <= hi; k++) {
+                const int ia = std::abs(i), ja = std::abs(j), ka = std::abs(k);
+                if (ia + ja + ka > Q) continue;
+                const int m = std::max(ia, std::max(ja, ka));
+                PlanCell pc;
+                pc.d[0] = (int8_t)i;
+                pc.d[1] = (int8_t)j;
+                pc.d[2] = (int8_t)k;
+                pc.pad = 0;
+                pc.flags = 0;
+                pc.nb[0] = pc.nb[1] = pc.nb[2] = pc.nb[3] = 0;
+                if (m == 0) {
+                    pc.flags = PC_SOURCE | PC_RATED;
+                    pc.wA = pc.wB = 0.0;
+                    pc.path = 0.5;  // raytracing.cu:290
+                    pc.np = 0.0;
+                } else {
+                    const int si = sign1(i), sj = sign1(j), sk = sign1(k);
+                    const int im = i - si, jm = j - sj, km = k - sk;
+                    int a, b, c;            // |minor A|, |minor B|, |dominant|
+                    int n1[3], n2[3], n3[3], n4[3];  // upstream cells c1..c4
+                    // dominant-axis selection with the reference's tie order (raytracing.cu:394,446,491)
+                    if (ka >= ja && ka >= ia) {
+                        a = ia; b = ja; c = ka;  // A = x, B = y (raytracing.cu:416-419)
+                        n1[0] = im; n1[1] = jm; n1[2] = km;
+                        n2[0] = i;  n2[1] = jm; n2[2] = km;
+                        n3[0] = im; n3[1] = j;  n3[2] = km;
+                        n4[0] = i;  n4[1] = j;  n4[2] = km;
+                    } else if (ja >= ia && ja >= ka) {
+                        a = ia; b = ka; c = ja;  // A = x, B = z (raytracing.cu:464-467)
+                        n1[0] = im; n1[1] = jm; n1[2] = km;
+                        n2[0] = i;  n2[1] = jm; n2[2] = km;
+                        n3[0] = im; n3[1] = jm; n3[2] = k;
+                        n4[0] = i;  n4[1] = jm; n4[2] = k;
+                    } else {
+                        a = ja; b = ka; c = ia;  // A = y, B = z (raytracing.cu:509-512)
+                        n1[0] = im; n1[1] = jm; n1[2] = km;
+                        n2[0] = im; n2[1] = j;  n2[2] = km;
+                        n3[0] = im; n3[1] = jm; n3[2] = k;
+                        n4[0] = im; n4[1] = j;  n4[2] = k;
+                    }
+                    // With dx = 1 - a/c (raytracing.cu:397-403 in source-relative coordinates) the
+                    // bilinear weights are s1 = wA*wB, s2 = wB*(1-wA), s3 = wA*(1-wB), s4 = (1-wA)*(1-wB).
+                    pc.wA = (double)a / (double)c;
+                    pc.wB = (double)b / (double)c;
+                    const double da = a, db = b, dc = c;
+                    pc.path = std::sqrt((da * da + db * db) / (dc * dc) + 1.0);  // raytracing.cu:444
+                    const int n = ia * ia + ja * ja + ka * ka;
+                    pc.np = (double)n * pc.path;
+                    if (c == 1 && (a == 1 || b == 1)) pc.flags |= (a == 1 && b == 1) ? PC_DIAG3 : PC_DIAG2;
+                    // Sphere test exactly as the reference kernel evaluates it (raytracing.cu:302-305,315),
+                    // nvcc contracting xs*xs+ys*ys+zs*zs into DMUL,DFMA,DFMA.
+                    const double xs = dr * (double)i, ys = dr * (double)j, zs = dr * (double)k;
+                    const double dist2 = std::fma(zs, zs, std::fma(ys, ys, xs * xs));
+                    if (dist2 / (dr * dr) <= R2) pc.flags |= PC_RATED;
+                    // upstream slots; zero-weight corners may fall outside the plan -> slot 0, weight 0
+                    const double s[4] = {pc.wA * pc.wB, pc.wB * (1.0 - pc.wA), pc.wA * (1.0 - pc.wB),
+                                         (1.0 - pc.wA) * (1.0 - pc.wB)};
+                    int* nn[4] = {n1, n2, n3, n4};
+                    for (int t = 0; t < 4; t++) {
+                        int sl = 0;
+                        if (s[t] != 0.0) {
+                            const int* q = nn[t];
+                            bool in = q[0] >= lo && q[0] <= hi && q[1] >= lo && q[1] <= hi && q[2] >= lo && q[2] <= hi;
+                            int32_t v = in ? slot[sidx(q[0], q[1], q[2])] : -1;
+                            int ml = std::max(std::abs(q[0]), std::max(std::abs(q[1]), std::abs(q[2])));
+                            if (v < 0 || ml != m - 1) {
+                                err = "sweep plan: internal error, upstream cell not in previous level";
+                                return false;
+                            }
+                            sl = v;
+                        }
+                        pc.nb[t] = (uint16_t)sl;
+                    }
+                }
+                plan.cells[plan.level_start[m] + slot[sidx(i, j, k)]] = pc;
+            }
+    plan.N = N;
+    plan.R = R;
+    plan.dr = dr;
+    plan.q_max = Q;
+    plan.nlevels = nlevels;
+    plan.max_level_cells = maxc;
+    plan.ncells = total;
+
+    cudaError_t e = cudaMalloc(&plan.d_cells, sizeof(PlanCell) * (size_t)total);
+    if (e == cudaSuccess) e = cudaMalloc(&plan.d_level_start, sizeof(int) * (nlevels + 1));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(plan.d_cells, plan.cells.data(), sizeof(PlanCell) * (size_t)total, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(plan.d_level_start, plan.level_start.data(), sizeof(int) * (nlevels + 1),
+                       cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        err = std::string("sweep plan upload: ") + cudaGetErrorString(e);
+        free_sweep_plan(plan);
+        return false;
+    }
+    plan.valid = true;
+    return true;
+}
+
+void free_sweep_plan(SweepPlan& plan)
+{
+    if (plan.d_cells) cudaFree(plan.d_cells);
+    if (plan.d_level_start) cudaFree(plan.d_level_start);
+    plan.d_cells = nullptr;
+    plan.d_level_start = nullptr;
+    plan.cells.clear();
+    plan.level_start.clear();
+    plan.valid = false;
+}

@@ -1,0 +1,161 @@
+"""The C2Ray time-step: iterate ray tracing and chemistry until the ionised fractions converge.
+
+Reference: pyc2ray/evolve.py -- evolve3D :38-245, evolve3D_MPI :249-498.  Same signatures, same
+convergence logic; what changes is where the data lives.  The reference crosses PCIe three times per
+iteration (H2D xh_av, D2H phi_ion, then the Fortran chemistry on the host plus two transposing
+copies).  Here ndens, temp, xh, xh_av, xh_intermed and phi_ion stay in HBM for the whole convergence
+loop; per iteration the host sees three scalars (conv_flag, sum x, sum 1-x).
+"""
+import ctypes
+import time
+
+import numpy as np
+
+from .asora_core import cuda_is_init
+from .lib import _cabi
+from .lib._cabi import L, check, dptr, iptr
+from .parallel import shard_bounds, allreduce_sum_, device_tensor
+from .utils import printlog
+from .utils.sourceutils import format_sources
+
+__all__ = ["evolve3D", "evolve3D_MPI", "evolve3D_dist"]
+
+
+def _flat(a):
+    """float64 flat copy in logical C order (index i*N*N + j*N + k), as evolve.py:142-143."""
+    return np.ravel(a).astype("float64", copy=True)
+
+
+def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table, minlogtau, dlogtau, R_max_LLS,
+                   convergence_fraction, sig, bh00, albpow, colh0, temph0, abu_c, logfile, quiet, shard=None,
+                   group=None, max_iter=10000):
+    if not cuda_is_init():
+        raise RuntimeError("GPU not initialized. Please initialize it by calling device_init(N)")
+    NumSrc_total = src_flux.shape[0]
+    N = temp.shape[0]
+    NumCells = N * N * N
+    NumTau = photo_thin_table.shape[0]
+    conv_criterion = min(int(convergence_fraction * NumCells), (NumSrc_total - 1) / 3)  # evolve.py:127
+    prev_sum_xh1_int = 2 * NumCells
+    prev_sum_xh0_int = 2 * NumCells
+
+    if shard is not None:
+        rank, nprocs = shard
+        i_start, i_end = shard_bounds(NumSrc_total, rank, nprocs)
+        srcpos_flat, normflux_flat = format_sources(src_pos[:, i_start:i_end], src_flux[i_start:i_end])
+    else:
+        rank, nprocs = 0, 1
+        srcpos_flat, normflux_flat = format_sources(src_pos, src_flux)
+    NumSrc = normflux_flat.shape[0]
+
+    check(L.asora_source_data_to_device(iptr(srcpos_flat), dptr(normflux_flat), NumSrc))
+    xh_flat = _flat(xh)
+    check(L.asora_buffer_upload(_cabi.BUF_NDENS, dptr(_flat(ndens))))
+    check(L.asora_buffer_upload(_cabi.BUF_TEMP, dptr(_flat(temp))))
+    for b in (_cabi.BUF_XH, _cabi.BUF_XH_AV, _cabi.BUF_XH_INTERMED):  # evolve.py:136-137
+        check(L.asora_buffer_upload(b, dptr(xh_flat)))
+    phi_t = None
+    if nprocs > 1:
+        phi_t = device_tensor(L.asora_device_buffer(_cabi.BUF_PHI_ION), NumCells)
+
+    if rank == 0:
+        printlog("Calling evolve3D..." if nprocs == 1 else f"Calling evolve3D with {nprocs:n} ranks...", logfile, quiet)
+        printlog(f"dr [Mpc]: {dr/3.086e24:.3e}", logfile, quiet)
+        printlog(f"dt [years]: {dt/3.15576E+07:.3e}", logfile, quiet)
+        printlog(f"Running on {NumSrc_total:n} source(s), total normalized ionizing flux: {src_flux.sum():.2e}", logfile, quiet)
+        printlog(f"Mean density (cgs): {ndens.mean():.3e}, Mean ionized fraction: {xh.mean():.3e}", logfile, quiet)
+        printlog(f"Convergence Criterion (Number of points): {conv_criterion : n}", logfile, quiet, end="\n\n")
+
+    converged = False
+    niter = 0
+    flag = ctypes.c_int(0)
+    s1 = ctypes.c_double(0.0)
+    s0 = ctypes.c_double(0.0)
+    while not converged:
+        niter += 1
+        trt0 = time.time()
+        check(L.asora_raytrace_device(float(R_max_LLS), float(sig), float(dr), 0, NumSrc, float(minlogtau),
+                                      float(dlogtau), int(NumTau), 1))
+        check(L.asora_sync())
+        if nprocs > 1:
+            import torch
+            allreduce_sum_(phi_t, group)  # evolve.py:433-437 (Reduce + Bcast) as one NCCL all-reduce
+            torch.cuda.synchronize()
+        trt = time.time() - trt0
+        tch0 = time.time()
+        check(L.asora_global_pass_device(float(dt), float(bh00), float(albpow), float(colh0), float(temph0),
+                                         float(abu_c), ctypes.byref(flag), ctypes.byref(s1), ctypes.byref(s0)))
+        tch = time.time() - tch0
+        conv_flag = flag.value
+        sum_xh1_int, sum_xh0_int = s1.value, s0.value
+        # evolve.py:216-232
+        rel_change_xh1 = abs((sum_xh1_int - prev_sum_xh1_int) / sum_xh1_int) if sum_xh1_int > 0.0 else 1.0
+        rel_change_xh0 = abs((sum_xh0_int - prev_sum_xh0_int) / sum_xh0_int) if sum_xh0_int > 0.0 else 1.0
+        if rank == 0:
+            printlog(f"Raytracing took {trt:.3f} s, chemistry {tch:.3f} s. Number of non-converged points: {conv_flag} "
+                     f"of {NumCells} ({conv_flag / NumCells * 100 : .3f} % ), Relative change in ionfrac: "
+                     f"{rel_change_xh1 : .2e}", logfile, quiet)
+        converged = (conv_flag < conv_criterion) or ((rel_change_xh1 < convergence_fraction) and
+                                                     (rel_change_xh0 < convergence_fraction))
+        prev_sum_xh1_int = sum_xh1_int
+        prev_sum_xh0_int = sum_xh0_int
+        if niter >= max_iter:
+            raise RuntimeError("evolve3D: no convergence")
+    if rank == 0:
+        printlog("Multiple source convergence reached.", logfile, quiet)
+    xh_new = np.empty(NumCells)
+    phi_ion = np.empty(NumCells)
+    check(L.asora_buffer_download(_cabi.BUF_XH_INTERMED, dptr(xh_new)))
+    check(L.asora_buffer_download(_cabi.BUF_PHI_ION, dptr(phi_ion)))
+    xh_new = xh_new.reshape(N, N, N)
+    if isinstance(xh, np.ndarray) and xh.flags.f_contiguous and not xh.flags.c_contiguous:
+        xh_new = np.asfortranarray(xh_new)  # np.copy(xh) keeps the order of xh (evolve.py:136-137,244)
+    evolve3D.last_niter = niter
+    return xh_new, phi_ion.reshape(N, N, N)
+
+
+def evolve3D(dt, dr, src_flux, src_pos, use_gpu, max_subbox, subboxsize, loss_fraction, temp, ndens, xh,
+             photo_thin_table, photo_thick_table, minlogtau, dlogtau, R_max_LLS, convergence_fraction, sig, bh00,
+             albpow, colh0, temph0, abu_c, logfile="pyC2Ray.log", quiet=False):
+    """Evolve the ionised fraction of the whole grid over one time step (evolve.py:38-245).
+
+    Arguments and return values as in the reference (xh_new, phi_ion).  ``use_gpu`` must be True;
+    the tables must have been copied with photo_table_to_device().  max_subbox, subboxsize and
+    loss_fraction only affect the reference's CPU ray tracer and are ignored.
+    """
+    if not use_gpu:
+        raise NotImplementedError("CPU ray tracing is not part of this build (use_gpu must be True)")
+    return _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table, minlogtau, dlogtau,
+                          R_max_LLS, convergence_fraction, sig, bh00, albpow, colh0, temph0, abu_c, logfile, quiet)
+
+
+evolve3D.last_niter = 0
+
+
+def evolve3D_dist(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table, photo_thick_table, minlogtau,
+                  dlogtau, R_max_LLS, convergence_fraction, sig, bh00, albpow, colh0, temph0, abu_c,
+                  logfile="pyC2Ray.log", quiet=False, group=None):
+    """Source-sharded time step over the ranks of an initialised torch.distributed process group
+    (backend nccl, one rank per GPU).  Every rank passes the full source list and gets the full
+    result."""
+    import torch.distributed as dist
+    rank, nprocs = dist.get_rank(group), dist.get_world_size(group)
+    shard = (rank, nprocs) if src_flux.shape[0] >= nprocs else None  # c2ray_base.py:185
+    return _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table, minlogtau, dlogtau,
+                          R_max_LLS, convergence_fraction, sig, bh00, albpow, colh0, temph0, abu_c, logfile,
+                          quiet or rank != 0, shard=shard, group=group)
+
+
+def evolve3D_MPI(dt, dr, src_flux, src_pos, use_gpu, max_subbox, subboxsize, loss_fraction, use_mpi, comm, rank,
+                 nprocs, temp, ndens, xh, photo_thin_table, photo_thick_table, minlogtau, dlogtau, R_max_LLS,
+                 convergence_fraction, sig, bh00, albpow, colh0, temph0, abu_c, logfile="pyC2Ray.log", quiet=False):
+    """Signature of the reference's MPI variant (evolve.py:249-258).  The mpi4py arguments are
+    accepted for compatibility; the exchange runs over the default torch.distributed group (NCCL),
+    which must have ``nprocs`` ranks with this process as ``rank``."""
+    import torch.distributed as dist
+    if not use_gpu:
+        raise NotImplementedError("CPU ray tracing is not part of this build (use_gpu must be True)")
+    if not dist.is_initialized() or dist.get_world_size() != nprocs or dist.get_rank() != rank:
+        raise RuntimeError("evolve3D_MPI: initialise torch.distributed (backend='nccl') with the same rank/size")
+    return evolve3D_dist(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table, photo_thick_table, minlogtau,
+                         dlogtau, R_max_LLS, convergence_fraction, sig, bh00, albpow, colh0, temph0, abu_c, logfile, quiet)

@@ -1,0 +1,78 @@
+"""Drop-in for the reference's CPython extension ``pyc2ray.lib.libasora``
+(src/asora/python_module.cu:153-161): the same six functions with the same positional signatures,
+implemented over the C ABI of libasora_b200.so.
+
+Like the reference wrappers, array arguments are taken as raw float64 / int32 buffers; unlike them,
+dtype, contiguity and size are checked, because a mismatch here would silently ray-trace garbage
+(python_module.cu:60-63 reads PyArray_DATA unchecked).
+"""
+import numpy as np
+
+from . import _cabi
+from ._cabi import L, check, dptr, iptr
+
+__all__ = ["do_all_sources", "device_init", "device_close", "density_to_device", "photo_table_to_device",
+           "source_data_to_device"]
+
+_N = None
+
+
+def _f64(a, name, size=None):
+    if not isinstance(a, np.ndarray) or a.dtype != np.float64:
+        raise TypeError(f"{name} must be Array of type double")
+    if not (a.flags.c_contiguous or a.flags.f_contiguous):
+        raise TypeError(f"{name} must be contiguous")
+    if size is not None and a.size < size:
+        raise ValueError(f"{name} has {a.size} elements, expected at least {size}")
+    return a
+
+
+def device_init(N, num_src_par):
+    """python_module.cu:73-82"""
+    global _N
+    check(L.asora_device_init(int(N), int(num_src_par)))
+    _N = int(N)
+
+
+def device_close():
+    """python_module.cu:87-92"""
+    global _N
+    check(L.asora_device_close())
+    _N = None
+
+
+def density_to_device(ndens, N):
+    """python_module.cu:97-109"""
+    _f64(ndens, "ndens", int(N) ** 3)
+    check(L.asora_density_to_device(dptr(ndens), int(N)))
+
+
+def photo_table_to_device(thin_table, thick_table, NumTau):
+    """python_module.cu:114-128"""
+    _f64(thin_table, "thin_table", int(NumTau))
+    _f64(thick_table, "thick_table", int(NumTau))
+    check(L.asora_photo_table_to_device(dptr(thin_table), dptr(thick_table), int(NumTau)))
+
+
+def source_data_to_device(pos, flux, NumSrc):
+    """python_module.cu:133-148"""
+    if not isinstance(pos, np.ndarray) or pos.dtype != np.int32 or not pos.flags.c_contiguous:
+        raise TypeError("pos must be a contiguous Array of type int32")
+    if pos.size < 3 * int(NumSrc):
+        raise ValueError("pos is shorter than 3*NumSrc")
+    _f64(flux, "flux", int(NumSrc))
+    check(L.asora_source_data_to_device(iptr(pos), dptr(flux), int(NumSrc)))
+
+
+def do_all_sources(R, coldensh_out, sig, dr, ndens, xh_av, phi_ion, NumSrc, m1, minlogtau, dlogtau, NumTau):
+    """python_module.cu:21-68.  ``coldensh_out`` and ``ndens`` are accepted and ignored exactly as the
+    reference ignores them (raytracing.cu:116); ``phi_ion`` is overwritten in place."""
+    if not isinstance(coldensh_out, np.ndarray) or coldensh_out.dtype != np.float64:
+        raise TypeError("coldensh_out must be Array of type double")  # python_module.cu:53-57
+    n3 = int(m1) ** 3
+    _f64(xh_av, "xh_av", n3)
+    _f64(phi_ion, "phi_ion", n3)
+    if not phi_ion.flags.writeable:
+        raise ValueError("phi_ion must be writeable")
+    check(L.asora_do_all_sources(float(R), float(sig), float(dr), dptr(xh_av), dptr(phi_ion), int(NumSrc),
+                                 int(m1), float(minlogtau), float(dlogtau), int(NumTau)))

@@ -1,0 +1,251 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs, and against the committed golden vectors.
+
+Tolerances (fp64 build; the north star allows 1e-5): the sweep re-associates a handful of products
+(interpolation fractions in source-relative form, 4*pi*dr^3 folded), so agreement with the oracle is
+expected at the 1e-12 level; rates are compared with rtol 1e-9 plus an absolute floor of 1e-12 of
+the largest rate in the box (cells whose thick-table difference cancels almost completely carry the
+reference's own log10 rounding noise).
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def libs():
+    import oracle
+    import pyc2ray_b200 as p
+    from pyc2ray_b200.lib import _cabi, libasora
+    return oracle, p, _cabi, libasora
+
+
+def _setup(libasora, c):
+    libasora.device_init(c["N"], 8)
+    libasora.photo_table_to_device(c["thin"], c["thick"], c["NumTau"])
+    libasora.density_to_device(np.ascontiguousarray(c["ndens"].ravel()), c["N"])
+    libasora.source_data_to_device(c["pos_flat"], c["flux_flat"], c["flux_flat"].size)
+
+
+def _sweep(libasora, _cabi, c, variant):
+    _cabi.check(_cabi.L.asora_set_sweep_variant(variant))
+    phi = np.zeros(c["N"] ** 3)
+    libasora.do_all_sources(c["R"], np.zeros(1), c["sig"], c["dr"], np.zeros(1), np.ascontiguousarray(c["xh"].ravel()),
+                            phi, c["flux_flat"].size, c["N"], c["minlogtau"], c["dlogtau"], c["NumTau"])
+    v = ctypes.c_int(0)
+    upd = ctypes.c_int64(0)
+    _cabi.L.asora_last_sweep_stats(ctypes.byref(v), None, ctypes.byref(upd), None, None, None)
+    _cabi.check(_cabi.L.asora_set_sweep_variant(0))
+    return phi, v.value, upd.value
+
+
+def _assert_close(a, b, what, rtol=RTOL, floor=1e-12):
+    atol = floor * np.max(np.abs(b))
+    bad = np.abs(a - b) > rtol * np.abs(b) + atol
+    rel = np.abs(a - b) / np.maximum(np.abs(b), atol)
+    assert not bad.any(), f"{what}: {bad.sum()} cells differ, max rel {rel.max():.3e}"
+    assert ((a != 0) == (b != 0)).all() or np.abs(a[(a != 0) != (b != 0)]).max() <= atol, f"{what}: support differs"
+    return rel.max()
+
+
+CASE_NAMES = ["small_r5", "clip_full_n24", "odd_n15_full", "r_int5", "multi_n32", "bench_like_n32", "thin_n24",
+              "mid_n48_r14"]
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+@pytest.mark.parametrize("variant", [1, 2])
+def test_phi_vs_oracle(libs, name, variant):
+    oracle, p, _cabi, libasora = libs
+    from tests.fields import make_case
+    c = make_case(name)
+    _setup(libasora, c)
+    try:
+        phi, used, upd = _sweep(libasora, _cabi, c, variant)
+    finally:
+        libasora.device_close()
+    assert used == variant
+    ref, _, n = oracle.asora_do_all_sources(c["R"], c["sig"], c["dr"], c["ndens"].ravel(), c["xh"].ravel(),
+                                            c["pos_flat"], c["flux_flat"], c["N"], c["thin"], c["thick"],
+                                            c["minlogtau"], c["dlogtau"], c["NumTau"])
+    assert upd == n
+    assert np.isfinite(phi).all()
+    _assert_close(phi, ref, f"{name} v{variant} phi_ion")
+
+
+@pytest.mark.parametrize("name", ["small_r5", "clip_full_n24", "multi_n32"])
+def test_phi_vs_committed_golden(libs, name):
+    oracle, p, _cabi, libasora = libs
+    from tests.fields import make_case, GOLDEN
+    g = np.load(os.path.join(GOLDEN, "oracle_sweep.npz"))
+    c = make_case(name)
+    _setup(libasora, c)
+    try:
+        phi, _, upd = _sweep(libasora, _cabi, c, 0)
+    finally:
+        libasora.device_close()
+    assert upd == int(g[name + "_n"])
+    _assert_close(phi, g[name + "_phi"], f"{name} vs golden")
+
+
+@pytest.mark.parametrize("name", ["small_r5", "clip_full_n24", "odd_n15_full"])
+@pytest.mark.parametrize("variant", [1, 2])
+def test_column_density_vs_oracle(libs, name, variant):
+    oracle, p, _cabi, libasora = libs
+    from tests.fields import make_case
+    c = make_case(name)
+    _setup(libasora, c)
+    try:
+        _cabi.check(_cabi.L.asora_set_sweep_variant(variant))
+        cdh = np.zeros(c["N"] ** 3)
+        phi = np.zeros(c["N"] ** 3)
+        xh = np.ascontiguousarray(c["xh"].ravel())
+        _cabi.check(_cabi.L.asora_debug_single_source(c["R"], c["sig"], c["dr"], _cabi.dptr(xh), 0, c["minlogtau"],
+                                                      c["dlogtau"], c["NumTau"], _cabi.dptr(cdh), _cabi.dptr(phi)))
+    finally:
+        _cabi.L.asora_set_sweep_variant(0)
+        libasora.device_close()
+    ref_phi, ref_cdh, _ = oracle.asora_do_all_sources(c["R"], c["sig"], c["dr"], c["ndens"].ravel(), c["xh"].ravel(),
+                                                      c["pos_flat"], c["flux_flat"], c["N"], c["thin"], c["thick"],
+                                                      c["minlogtau"], c["dlogtau"], c["NumTau"])
+    assert ((cdh != 0) == (ref_cdh != 0)).all(), "visited-cell sets differ"
+    np.testing.assert_allclose(cdh, ref_cdh, rtol=1e-12, atol=0)
+    _assert_close(phi, ref_phi, f"{name} v{variant} phi (debug path)")
+
+
+def test_variants_agree_and_superpose(libs):
+    """Properties that hold at any size: the two sweep variants agree; phi is linear in the fluxes and
+    additive over disjoint source subsets."""
+    oracle, p, _cabi, libasora = libs
+    from tests.fields import make_case
+    c = make_case("multi_n32")
+    _setup(libasora, c)
+    try:
+        phi1, _, _ = _sweep(libasora, _cabi, c, 1)
+        phi2, _, _ = _sweep(libasora, _cabi, c, 2)
+        _assert_close(phi1, phi2, "variant 1 vs 2", rtol=1e-11)
+        ns = c["flux_flat"].size
+        libasora.source_data_to_device(c["pos_flat"], 2.0 * c["flux_flat"], ns)
+        phid, _, _ = _sweep(libasora, _cabi, c, 0)
+        _assert_close(phid, 2.0 * phi1, "linearity in flux", rtol=1e-12)
+        h = ns // 2
+        libasora.source_data_to_device(np.ascontiguousarray(c["pos_flat"][:3 * h]), np.ascontiguousarray(c["flux_flat"][:h]), h)
+        ca = dict(c, flux_flat=c["flux_flat"][:h])
+        pa, _, _ = _sweep(libasora, _cabi, ca, 0)
+        libasora.source_data_to_device(np.ascontiguousarray(c["pos_flat"][3 * h:]), np.ascontiguousarray(c["flux_flat"][h:]), ns - h)
+        cb = dict(c, flux_flat=c["flux_flat"][h:])
+        pb, _, _ = _sweep(libasora, _cabi, cb, 0)
+        _assert_close(pa + pb, phi1, "additivity over source subsets", rtol=1e-11)
+    finally:
+        libasora.device_close()
+
+
+def test_chemistry_vs_oracle(libs):
+    oracle, p, _cabi, libasora = libs
+    from pyc2ray_b200.lib import libc2ray
+    rng = np.random.default_rng(5)
+    shape = (20, 20, 20)
+    ndens = np.asfortranarray(1e-3 * np.exp(rng.normal(size=shape)))
+    temp = np.asfortranarray(np.full(shape, 1e4) * rng.uniform(0.5, 2.0, size=shape))
+    xh = np.asfortranarray(rng.uniform(1e-4, 0.9, size=shape))
+    phi = np.asfortranarray(10 ** rng.uniform(-16, -11, size=shape))
+    phi[rng.uniform(size=shape) < 0.2] = 0.0
+    for dt_yr in (1e5, 1e6, 1e7):
+        dt = dt_yr * 3.15576e7
+        args = (2.59e-13, -0.7, 1.3e-8 * 0.83 / 13.598 ** 2, 13.598 / 8.617e-5, 7.1e-7)
+        xa_o, xi_o = xh.copy(order="F"), xh.copy(order="F")
+        f_o = oracle.global_pass(dt, ndens, temp, xh, xa_o, xi_o, phi, *args)
+        xa_g, xi_g = xh.copy(order="F"), xh.copy(order="F")
+        f_g = libc2ray.chemistry.global_pass(dt, ndens, temp, xh, xa_g, xi_g, phi, *args)
+        assert f_g == f_o
+        np.testing.assert_allclose(xi_g, xi_o, rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(xa_g, xa_o, rtol=1e-12, atol=1e-300)
+
+
+def test_chemistry_tutorial_known_answer(libs):
+    """tutorials/chemistry_solver.ipynb cells 3,5: mean x 0.050 -> 0.127 after 100 x 50 yr."""
+    oracle, p, _cabi, libasora = libs
+    np.random.seed(2023)
+    shape = (10, 10, 10)
+    ndens = np.random.normal(loc=1e-7, scale=1e-8, size=shape)
+    temp = np.ones(shape) * 1e4
+    xh = np.random.uniform(low=0, high=0.1, size=shape)
+    phi_ion = np.random.uniform(low=1e-13, high=1e-12, size=shape)
+    assert "%.3f" % np.mean(xh) == "0.050"
+    for _ in range(100):
+        xh = p.chemistry.hydrogenODE(dt=50 * 3.15576e7, ndens=ndens, temp=temp, xh=xh, phi_ion=phi_ion)
+    assert "%.3f" % np.mean(xh) == "0.127"
+
+
+def _cpu_evolve(oracle, c, dt, temp, conv_frac, chem):
+    """evolve.py:125-245 with the oracle in both roles."""
+    N = c["N"]
+    xh = c["xh"]
+    NumSrc = c["flux_flat"].size
+    conv_criterion = min(int(conv_frac * N ** 3), (NumSrc - 1) / 3)
+    prev1 = prev0 = 2 * N ** 3
+    xh_av, xh_int = xh.copy(), xh.copy()
+    niter = 0
+    while True:
+        niter += 1
+        phi, _, _ = oracle.asora_do_all_sources(c["R"], c["sig"], c["dr"], c["ndens"].ravel(), xh_av.ravel(),
+                                                c["pos_flat"], c["flux_flat"], N, c["thin"], c["thick"],
+                                                c["minlogtau"], c["dlogtau"], c["NumTau"])
+        phi = phi.reshape(N, N, N)
+        flag = oracle.global_pass(dt, c["ndens"], temp, xh, xh_av, xh_int, phi, *chem)
+        s1, s0 = xh_int.sum(), (1.0 - xh_int).sum()
+        r1 = abs((s1 - prev1) / s1) if s1 > 0 else 1.0
+        r0 = abs((s0 - prev0) / s0) if s0 > 0 else 1.0
+        prev1, prev0 = s1, s0
+        if flag < conv_criterion or (r1 < conv_frac and r0 < conv_frac):
+            return xh_int, phi, niter
+
+
+def test_evolve3D_vs_cpu_loop(libs):
+    oracle, p, _cabi, libasora = libs
+    from tests.fields import make_case
+    c = make_case("multi_n32")
+    c["ndens"] = np.ascontiguousarray(c["ndens"])
+    c["xh"] = np.full_like(c["ndens"], 2e-4)
+    c["flux_flat"] = c["flux_flat"] * 1e6
+    c["flux"] = c["flux"] * 1e6
+    N = c["N"]
+    temp = np.full((N, N, N), 1e4)
+    chem = (2.59e-13, -0.7, 1.3e-8 * 0.83 / 13.598 ** 2, 13.598 / 8.617e-5, 7.1e-7)
+    dt = 1e6 * 3.15576e7
+    p.device_init(N, 8)
+    try:
+        p.photo_table_to_device(c["thin"], c["thick"])
+        x_g, phi_g = p.evolve3D(dt, c["dr"], c["flux"], c["srcpos"], True, 1000, 100, 1e-2, temp, c["ndens"], c["xh"],
+                                c["thin"], c["thick"], c["minlogtau"], c["dlogtau"], c["R"], 1e-4, c["sig"], *chem,
+                                logfile=None, quiet=True)
+        nit_g = p.evolve3D.last_niter
+    finally:
+        p.device_close()
+    x_c, phi_c, nit_c = _cpu_evolve(oracle, c, dt, temp, 1e-4, chem)
+    assert nit_g == nit_c
+    assert x_g.mean() > 10 * 2e-4, "test must actually ionise something"
+    np.testing.assert_allclose(x_g, x_c, rtol=1e-8, atol=1e-14)
+    _assert_close(phi_g.ravel(), phi_c.ravel(), "evolve3D phi_ion", rtol=1e-7)
+
+
+def test_errors_are_reported_not_thrown(libs):
+    oracle, p, _cabi, libasora = libs
+    with pytest.raises(RuntimeError, match="not initialized"):
+        libasora.density_to_device(np.zeros(8), 2)
+    libasora.device_init(8, 1)
+    try:
+        with pytest.raises(RuntimeError, match="photo tables"):
+            libasora.source_data_to_device(np.zeros(3, dtype=np.int32), np.ones(1), 1)
+            libasora.do_all_sources(3.0, np.zeros(1), 6.3e-18, 1e20, np.zeros(1), np.zeros(512), np.zeros(512), 1, 8,
+                                    -20.0, 0.012, 2001)
+        with pytest.raises(TypeError):
+            libasora.do_all_sources(3.0, np.zeros(1, dtype=np.float32), 6.3e-18, 1e20, np.zeros(1), np.zeros(512),
+                                    np.zeros(512), 1, 8, -20.0, 0.012, 2001)
+    finally:
+        libasora.device_close()
