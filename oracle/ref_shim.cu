@@ -25,7 +25,15 @@ int ref_device_init(int N, int num_src_par)
 void ref_device_close(void) { device_close(); }
 void ref_density_to_device(double* ndens, int N) { density_to_device(ndens, N); }
 void ref_photo_table_to_device(double* thin, double* thick, int NumTau) { photo_table_to_device(thin, thick, NumTau); }
-void ref_source_data_to_device(int* pos, double* flux, int NumSrc) { source_data_to_device(pos, flux, NumSrc); }
+// source_data_to_device frees the previous pointers first (memory.cu:102-103); after a
+// device_close()/device_init() cycle in one process those are dangling, cudaFree fails with
+// cudaErrorInvalidValue, and the reference later reports that stale error as a launch failure
+// (raytracing.cu:134).  The harness drops the stale error; the reference code is untouched.
+void ref_source_data_to_device(int* pos, double* flux, int NumSrc)
+{
+    source_data_to_device(pos, flux, NumSrc);
+    (void)cudaGetLastError();
+}
 int ref_do_all_sources(double R, double* coldensh_out, double sig, double dr, double* ndens, double* xh_av,
                        double* phi_ion, int NumSrc, int m1, double minlogtau, double dlogtau, int NumTau)
 {

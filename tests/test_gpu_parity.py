@@ -16,6 +16,10 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-9
+# Optically thin cells use prefact*(tau_out - tau_in)*T_thin (rates.cu:37): tau_out - tau_in cancels
+# to ~eps*tau/dtau, so any change in FMA contraction moves the result by that much.  The reference's
+# own CPU and GPU builds differ from each other at this level.
+CASE_RTOL = {"thin_n24": 1e-6}
 
 
 @pytest.fixture(scope="module")
@@ -75,7 +79,7 @@ def test_phi_vs_oracle(libs, name, variant):
                                             c["minlogtau"], c["dlogtau"], c["NumTau"])
     assert upd == n
     assert np.isfinite(phi).all()
-    _assert_close(phi, ref, f"{name} v{variant} phi_ion")
+    _assert_close(phi, ref, f"{name} v{variant} phi_ion", rtol=CASE_RTOL.get(name, RTOL))
 
 
 @pytest.mark.parametrize("name", ["small_r5", "clip_full_n24", "multi_n32"])

