@@ -111,6 +111,12 @@ int asora_global_pass_device(double dt, double bh00, double albpow, double colh0
 /* Wait for all work queued on the context's stream. */
 int asora_sync(void);
 
+/* Run all subsequent work of the context on a caller-owned CUDA stream (a cudaStream_t passed as an
+ * opaque pointer; NULL restores the context's own stream).  Lets a caller order the sweep with its
+ * own work -- e.g. an NCCL all-reduce of PHI_ION -- without host synchronisation, and time both with
+ * events on one stream. */
+int asora_set_stream(void* cuda_stream);
+
 /* ---- diagnostics -------------------------------------------------------------------------------- */
 
 /* Ray-trace ONE uploaded source and return its outgoing column density grid (host, N^3; cells the
@@ -122,6 +128,10 @@ int asora_debug_single_source(double R, double sig, double dr, const double* xh_
 /* Force the sweep variant: 0 = automatic, 1 = shared-memory level sweep (one CTA per source batch),
  * 2 = grid-cooperative level sweep (whole GPU per source).  Returns non-zero for unknown values. */
 int asora_set_sweep_variant(int variant);
+
+/* Override the launch shape of the shared-memory sweep: sources per CTA (1, 2 or 4) and threads per
+ * CTA (multiple of 32, <= 1024); 0 = automatic.  For tuning and profiling. */
+int asora_set_tuning(int sources_per_cta, int block_threads);
 
 /* Statistics of the most recent ray trace: variant used, number of kernel launches, number of
  * (source, cell) updates, q_max, number of Chebyshev levels, device milliseconds (CUDA events on

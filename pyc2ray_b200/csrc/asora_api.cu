@@ -7,6 +7,7 @@
 #include "asora_common.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -19,7 +20,8 @@ struct Context {
     int device = 0;
     int sm_count = 0;
     int smem_optin = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // the stream work is queued on
+    cudaStream_t own_stream = nullptr;  // created by device_init; `stream` unless the caller set one
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double* buf[ASORA_BUF_COUNT] = {nullptr};
     double* thin = nullptr;
@@ -38,6 +40,7 @@ struct Context {
     int64_t chem_stage_n = 0;
     // stats of the last sweep
     int variant_forced = 0;
+    int tune_S = 0, tune_block = 0;
     int last_variant = 0, last_launches = 0, last_qmax = 0, last_levels = 0;
     int64_t last_updates = 0;
     float last_ms = 0.f;
@@ -152,12 +155,13 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
             if (per_src > budget) {
                 plan_ok = false;
             } else {
-                // sources per CTA: amortise the plan over S sources while keeping >= 2 CTAs per SM
+                // Launch shape (measured on B200, scripts/perf_probe.py): one source per CTA; 256 threads
+                // while a level is at most a few passes wide, 1024 once levels reach thousands of cells.
                 S = 1;
-                if (count >= 4 * g.sm_count && 4 * per_src * 2 <= budget) S = 4;
-                else if (count >= 2 * g.sm_count && 2 * per_src * 2 <= budget) S = 2;
                 const int maxc = g.plan.max_level_cells;
-                block = maxc >= 4096 ? 1024 : (maxc >= 1024 ? 512 : 256);
+                block = maxc >= 2048 ? 1024 : 256;
+                if (g.tune_S > 0 && (size_t)g.tune_S * per_src <= budget) S = g.tune_S;
+                if (g.tune_block > 0) block = g.tune_block;
             }
         }
         if (variant == 1 && !plan_ok) return fail("sweep variant 1 forced but a level does not fit in shared memory");
@@ -204,7 +208,8 @@ int asora_device_init(int N, int num_src_par)
     CK(cudaDeviceGetAttribute(&g.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, g.device));
     g.N = N;
     g.ncell = (int64_t)N * N * N;
-    CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
+    g.stream = g.own_stream;
     CK(cudaEventCreate(&g.ev0));
     CK(cudaEventCreate(&g.ev1));
     g.init = true;
@@ -213,10 +218,14 @@ int asora_device_init(int N, int num_src_par)
     if (int rc = ensure_buffer(ASORA_BUF_XH_AV)) return rc;
     if (int rc = ensure_buffer(ASORA_BUF_PHI_ION)) return rc;
     CK(cudaStreamSynchronize(g.stream));
-    printf("GPU Device %d: \"%s\" with compute capability %d.%d\n", g.device, prop.name, prop.major, prop.minor);
-    printf("Succesfully allocated %g Mb of device memory for grid of size N = %d (column densities stay on-chip)\n",
-           3.0 * g.ncell * sizeof(double) / 1e6, N);
-    fflush(stdout);
+    // the reference prints the device and the allocation (memory.cu:52-59,77-78); ASORA_QUIET=1 silences it
+    const char* quiet = getenv("ASORA_QUIET");
+    if (!(quiet && quiet[0] == '1')) {
+        printf("GPU Device %d: \"%s\" with compute capability %d.%d\n", g.device, prop.name, prop.major, prop.minor);
+        printf("Succesfully allocated %g Mb of device memory for grid of size N = %d (column densities stay on-chip)\n",
+               3.0 * g.ncell * sizeof(double) / 1e6, N);
+        fflush(stdout);
+    }
     return 0;
 }
 
@@ -248,9 +257,9 @@ int asora_device_close(void)
     free_sweep_plan(g.plan);
     if (g.ev0) cudaEventDestroy(g.ev0);
     if (g.ev1) cudaEventDestroy(g.ev1);
-    if (g.stream) cudaStreamDestroy(g.stream);
+    if (g.own_stream) cudaStreamDestroy(g.own_stream);
     g.ev0 = g.ev1 = nullptr;
-    g.stream = nullptr;
+    g.stream = g.own_stream = nullptr;
     g.init = false;
     return 0;
 }
@@ -348,6 +357,14 @@ int asora_sync(void)
     return 0;
 }
 
+int asora_set_stream(void* cuda_stream)
+{
+    if (int rc = need_init()) return rc;
+    CK(cudaStreamSynchronize(g.stream));
+    g.stream = cuda_stream ? (cudaStream_t)cuda_stream : g.own_stream;
+    return 0;
+}
+
 void* asora_device_buffer(int which)
 {
     if (need_init()) return nullptr;
@@ -437,6 +454,16 @@ int asora_set_sweep_variant(int variant)
 {
     if (variant < 0 || variant > 2) return fail("set_sweep_variant: unknown variant");
     g.variant_forced = variant;
+    return 0;
+}
+
+int asora_set_tuning(int sources_per_cta, int block_threads)
+{
+    if (!(sources_per_cta == 0 || sources_per_cta == 1 || sources_per_cta == 2 || sources_per_cta == 4))
+        return fail("set_tuning: sources_per_cta must be 0, 1, 2 or 4");
+    if (block_threads < 0 || block_threads > 1024 || block_threads % 32) return fail("set_tuning: bad block size");
+    g.tune_S = sources_per_cta;
+    g.tune_block = block_threads;
     return 0;
 }
 

@@ -33,8 +33,10 @@ SIGNATURES = {
     "asora_raytrace_device": (_i, [_d, _d, _d, _i, _i, _d, _d, _i, _i]),
     "asora_global_pass_device": (_i, [_d, _d, _d, _d, _d, _d, ctypes.POINTER(_i), c_dp, c_dp]),
     "asora_sync": (_i, []),
+    "asora_set_stream": (_i, [ctypes.c_void_p]),
     "asora_debug_single_source": (_i, [_d, _d, _d, c_dp, _i, _d, _d, _i, c_dp, c_dp]),
     "asora_set_sweep_variant": (_i, [_i]),
+    "asora_set_tuning": (_i, [_i, _i]),
     "asora_last_sweep_stats": (_i, [ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i64),
                                     ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_float)]),
     "asora_cells_per_source": (_i64, [_i, _d]),
