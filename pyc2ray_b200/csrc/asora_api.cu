@@ -24,9 +24,11 @@ struct Context {
     cudaStream_t own_stream = nullptr;  // created by device_init; `stream` unless the caller set one
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double* buf[ASORA_BUF_COUNT] = {nullptr};
-    double* thin = nullptr;
-    double* thick = nullptr;
+    double2* thin = nullptr;   // {T[i], T[i+1]-T[i]} pairs (sweep_kernels.cu: photo_lookup)
+    double2* thick = nullptr;
     int ntab = 0;
+    double* nhi = nullptr;      // ndens * (1 - xh_av), rebuilt before every sweep
+    double2* log2_tab = nullptr;
     int* src_pos = nullptr;
     double* src_flux = nullptr;
     int nsrc = 0;
@@ -41,6 +43,7 @@ struct Context {
     // stats of the last sweep
     int variant_forced = 0;
     int tune_S = 0, tune_block = 0;
+    int last_launches_prep = 0;
     int last_variant = 0, last_launches = 0, last_qmax = 0, last_levels = 0;
     int64_t last_updates = 0;
     float last_ms = 0.f;
@@ -102,6 +105,18 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     if (int rc = ensure_buffer(ASORA_BUF_XH_AV)) return rc;
     if (int rc = ensure_buffer(ASORA_BUF_PHI_ION)) return rc;
     const int N = g.N;
+    if (!g.nhi) CK(cudaMalloc(&g.nhi, sizeof(double) * g.ncell));
+    if (!g.log2_tab) {
+        double h[512];
+        host_log2_table(h);
+        CK(cudaMalloc(&g.log2_tab, sizeof(h)));
+        CK(cudaMemcpy(g.log2_tab, h, sizeof(h), cudaMemcpyHostToDevice));
+    }
+    {
+        cudaError_t e = launch_prepare_nhi(g.buf[ASORA_BUF_NDENS], g.buf[ASORA_BUF_XH_AV], g.nhi, g.ncell, g.stream);
+        if (e != cudaSuccess) return fail_cuda("prepare_nhi_kernel launch", e);
+        g.last_launches_prep = 1;
+    }
     if (zero_phi) CK(cudaMemsetAsync(g.buf[ASORA_BUF_PHI_ION], 0, sizeof(double) * g.ncell, g.stream));
 
     SweepParams p;
@@ -112,14 +127,16 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     p.R2 = R * R;
     p.sig = sig;
     p.dr = dr;
-    p.dr3 = dr * dr * dr;
-    p.volfac = ASORA_FOURPI * p.dr3;
+    p.inv_volfac = 1.0 / (ASORA_FOURPI * (dr * dr * dr));
+    // rates.cu:77-78: index = 1 + (log10(tau) - minlogtau)/dlogtau = lut_a + lut_b * log2(tau)
+    p.lut_b = 0.30102999566398119521 / dlogtau;
+    p.lut_a = 1.0 - minlogtau / dlogtau;
     p.minlogtau = minlogtau;
     p.dlogtau = dlogtau;
     p.NumTau = NumTau;
     p.ntab = g.ntab;
-    p.ndens = g.buf[ASORA_BUF_NDENS];
-    p.xh_av = g.buf[ASORA_BUF_XH_AV];
+    p.nhi = g.nhi;
+    p.log2_tab = g.log2_tab;
     p.phi_ion = g.buf[ASORA_BUF_PHI_ION];
     p.thin = g.thin;
     p.thick = g.thick;
@@ -130,7 +147,7 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     p.coldens_out = coldens_grid;
 
     g.last_qmax = p.q_max;
-    g.last_launches = 0;
+    g.last_launches = g.last_launches_prep;
     g.last_updates = (int64_t)count * asora_count_cells(N, R);
     g.last_ms = 0.f;
 
@@ -239,6 +256,10 @@ int asora_device_close(void)
     }
     if (g.thin) cudaFree(g.thin);
     if (g.thick) cudaFree(g.thick);
+    if (g.nhi) cudaFree(g.nhi);
+    if (g.log2_tab) cudaFree(g.log2_tab);
+    g.nhi = nullptr;
+    g.log2_tab = nullptr;
     if (g.src_pos) cudaFree(g.src_pos);
     if (g.src_flux) cudaFree(g.src_flux);
     if (g.chem_partials) cudaFree(g.chem_partials);
@@ -279,11 +300,17 @@ int asora_photo_table_to_device(const double* thin_table, const double* thick_ta
     if (g.thin) cudaFree(g.thin);
     if (g.thick) cudaFree(g.thick);
     g.thin = g.thick = nullptr;
-    CK(cudaMalloc(&g.thin, sizeof(double) * NumTau));
-    CK(cudaMalloc(&g.thick, sizeof(double) * NumTau));
-    CK(cudaMemcpyAsync(g.thin, thin_table, sizeof(double) * NumTau, cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemcpyAsync(g.thick, thick_table, sizeof(double) * NumTau, cudaMemcpyHostToDevice, g.stream));
+    double* raw = nullptr;
+    CK(cudaMalloc(&raw, sizeof(double) * 2 * (size_t)NumTau));
+    CK(cudaMalloc(&g.thin, sizeof(double2) * NumTau));
+    CK(cudaMalloc(&g.thick, sizeof(double2) * NumTau));
+    CK(cudaMemcpyAsync(raw, thin_table, sizeof(double) * NumTau, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(raw + NumTau, thick_table, sizeof(double) * NumTau, cudaMemcpyHostToDevice, g.stream));
+    cudaError_t e = launch_pair_table(raw, g.thin, NumTau, g.stream);
+    if (e == cudaSuccess) e = launch_pair_table(raw + NumTau, g.thick, NumTau, g.stream);
+    if (e != cudaSuccess) return fail_cuda("pair_table_kernel launch", e);
     CK(cudaStreamSynchronize(g.stream));
+    cudaFree(raw);
     g.ntab = NumTau;
     return 0;
 }

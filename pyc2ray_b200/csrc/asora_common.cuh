@@ -34,7 +34,8 @@
 struct __align__(16) PlanCell {
     double wA, wB;   // |minor offset| / |dominant offset| for the two minor axes
     double path;     // path length through the cell in cell units (raytracing.cu:444,489,533)
-    double np;       // (di^2+dj^2+dk^2) * path ; vol_ph = 4 pi dr^3 * np (raytracing.cu:300-307)
+    double inv_np;   // 1 / ((di^2+dj^2+dk^2) * path): 1/vol_ph = inv_np / (4 pi dr^3) (raytracing.cu:300-307);
+                     // 4 pi for the source cell, whose volume is dr^3 (raytracing.cu:292)
     uint16_t nb[4];  // slots, in the previous level, of the 4 upstream cells c1..c4
     int8_t d[3];     // offset from the source
     uint8_t flags;
@@ -63,16 +64,16 @@ struct SweepParams {
     int last_l, last_r;       // raytracing.cu:122-123
     double R2;                // R*R
     double sig, dr;
-    double dr3;               // dr*dr*dr (source-cell volume, raytracing.cu:292)
-    double volfac;            // 4 pi dr^3
+    double inv_volfac;        // 1 / (4 pi dr^3)
+    double lut_a, lut_b;      // table index = lut_a + lut_b * log2(tau)  (rates.cu:77-78)
     double minlogtau, dlogtau;
     int NumTau;               // index clamp as passed by the caller (rates.cu:78-79)
     int ntab;                 // uploaded table length
-    const double* ndens;
-    const double* xh_av;
+    const double* nhi;        // ndens * (1 - xh_av), refreshed before every sweep (raytracing.cu:275-276)
     double* phi_ion;
-    const double* thin;
-    const double* thick;
+    const double2* thin;      // {T[i], T[i+1]-T[i]} pairs of the uploaded tables
+    const double2* thick;
+    const double2* log2_tab;  // 256 x {1/c_j, log2 c_j}, c_j the centre of mantissa bin j
     const int* src_pos;
     const double* src_flux;
     int src_begin, src_count;
@@ -91,6 +92,10 @@ size_t sweep_smem_bytes(const SweepPlan& plan, int sources_per_cta);
 cudaError_t launch_sweep_smem(const SweepPlan& plan, const SweepParams& p, int sources_per_cta, int block,
                               cudaStream_t stream, int* launches);
 cudaError_t launch_sweep_grid(const SweepParams& p, cudaStream_t stream, int* launches, int* levels);
+
+cudaError_t launch_prepare_nhi(const double* ndens, const double* xh_av, double* nhi, int64_t ncell, cudaStream_t stream);
+cudaError_t launch_pair_table(const double* table, double2* pairs, int ntab, cudaStream_t stream);
+void host_log2_table(double* tab512);
 
 // chemistry.cu
 cudaError_t launch_global_pass(double dt, const double* ndens, const double* temp, const double* xh,

@@ -12,54 +12,97 @@
 //                         grid-wide barrier per level; column densities go through an N^3 scratch
 //                         grid that stays in the 126 MB L2.  Geometry is computed on the fly.  Used
 //                         when a level does not fit in shared memory (large radii / full box).
+//
+// Arithmetic.  The first B200 profile of a literal transcription (profiles/r01_*) showed ~440
+// thread-instructions per source-cell update, dominated by the CUDA library's fp64 division (nine per
+// update) and log10 (two per update) call sequences, with the fp64 pipe only 33-40 % busy.  The
+// per-cell arithmetic below is the same real-number computation re-associated so that one update needs
+// two reciprocals and two table-driven logarithms:
+//   * the four weightf() divisions and the normalisation of raytracing.cu:422-428 become one
+//     division of products (interp_coldens);
+//   * strength/Vfact and phi/nHI (rates.cu:24, raytracing.cu:324) share one division;
+//   * log10(tau) -> table index (rates.cu:77-78) is index = a + b*log2(tau) with log2 from a
+//     256-entry mantissa table in shared memory and a degree-6 polynomial (|error| < 2 ulp);
+//   * T[i0] + r*(T[i1]-T[i0]) reads one 16-byte {T[i], T[i+1]-T[i]} pair.
+// Results agree with the reference's own expression order to ~1e-13 relative (tests/).
 #include "asora_common.cuh"
 
 #include <cooperative_groups.h>
+#include <cmath>
 namespace cg = cooperative_groups;
+
+// ---------------------------------------------------------------------------------------------------
+// fp64 helpers
+// ---------------------------------------------------------------------------------------------------
+
+// 1/x for a normal, finite x: MUFU.RCP64H seed (>= 20 bits) + one cubic and one quadratic Newton step.
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    e = fma(e, e, e);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
+// a/b with a final residual correction (<= 1 ulp for normal operands)
+__device__ __forceinline__ double fast_div(double a, double b)
+{
+    const double r = fast_rcp(b);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+}
+
+// log2(x), x normal and positive.  tab[j] = {1/c_j, log2 c_j} for the 256 mantissa bins of [1,2).
+__device__ __forceinline__ double fast_log2(double x, const double2* __restrict__ tab)
+{
+    const int hi = __double2hiint(x), lo = __double2loint(x);
+    const int e = (hi >> 20) - 1023;
+    const double2 t = tab[(hi >> 12) & 0xff];
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    const double r = fma(m, t.x, -1.0);  // |r| <= 2^-9
+    // log2(1+r) = r * (c1 + c2 r + ... + c6 r^5), c_k = (-1)^(k+1) / (k ln 2)
+    double p = fma(r, -0.24044917348149391, 0.28853900817779268);
+    p = fma(r, p, -0.36067376022224085);
+    p = fma(r, p, 0.48089834696298783);
+    p = fma(r, p, -0.72134752044448170);
+    p = fma(r, p, 1.44269504088896341);
+    return fma(r, p, (double)e + t.y);
+}
+
+void host_log2_table(double* tab512)
+{
+    for (int j = 0; j < 256; j++) {
+        const long double c = 1.0L + ((long double)j + 0.5L) / 256.0L;
+        const double inv = (double)(1.0L / c);
+        tab512[2 * j + 0] = inv;
+        tab512[2 * j + 1] = (double)(-log2l((long double)inv));  // log2 of the value 1/inv actually used
+    }
+}
 
 // ---------------------------------------------------------------------------------------------------
 // per-cell arithmetic
 // ---------------------------------------------------------------------------------------------------
 
-// rates.cu:70-83.  `ntab` additionally clamps to the uploaded table length (reference bug N6: the
-// Python callers pass NumTau = table length, which lets i1 reach one element past the table).
-__device__ __forceinline__ double photo_lookuptable(const double* __restrict__ table, double tau,
-                                                    double minlogtau, double dlogtau, int NumTau, int ntab)
+// rates.cu:70-83 with index = lut_a + lut_b*log2(tau).  `ntab` additionally clamps to the uploaded
+// table length (reference bug N6: Python callers pass NumTau = table length, which lets i1 reach one
+// element past the table); the pair table's last slope is 0, which is the same clamp.
+__device__ __forceinline__ double photo_lookup(const double2* __restrict__ pairs, double log2tau, const SweepParams& p)
 {
-    double logtau = log10(fmax(1.0e-20, tau));
-    double real_i = fmin((double)NumTau, fmax(0.0, 1.0 + (logtau - minlogtau) / dlogtau));
+    const double real_i = fmin((double)p.NumTau, fmax(0.0, fma(p.lut_b, log2tau, p.lut_a)));
     int i0 = (int)real_i;
-    int i1 = min(NumTau, i0 + 1);
-    double residual = real_i - (double)i0;
-    i0 = min(i0, ntab - 1);
-    i1 = min(i1, ntab - 1);
-    double t0 = __ldg(table + i0), t1 = __ldg(table + i1);
-    return t0 + residual * (t1 - t0);
+    const double residual = real_i - (double)i0;
+    i0 = min(i0, p.ntab - 1);
+    const double2 t = __ldg(pairs + i0);
+    return fma(residual, t.y, t.x);
 }
 
-// rates.cu:16-41
-__device__ __forceinline__ double photoion_rate(double strength, double coldens_in, double coldens_out,
-                                                double Vfact, const SweepParams& p)
-{
-    double tau_in = coldens_in * p.sig;
-    double tau_out = coldens_out * p.sig;
-    double prefact = strength / Vfact;
-    double phi_photo_in = prefact * photo_lookuptable(p.thick, tau_in, p.minlogtau, p.dlogtau, p.NumTau, p.ntab);
-    if (fabs(tau_out - tau_in) > ASORA_TAU_PHOTO_LIMIT) {
-        double phi_photo_out =
-            prefact * photo_lookuptable(p.thick, tau_out, p.minlogtau, p.dlogtau, p.NumTau, p.ntab);
-        return phi_photo_in - phi_photo_out;
-    }
-    return prefact * (tau_out - tau_in) *
-           photo_lookuptable(p.thin, tau_out, p.minlogtau, p.dlogtau, p.NumTau, p.ntab);
-}
-
-// raytracing.cu:33
-__device__ __forceinline__ double weightf(double cd, double sig) { return 1.0 / fmax(0.6, cd * sig); }
-
-// raytracing.cu:405-441 with s1..s4 written in terms of the minor-axis fractions (sweep_plan.cu).
-// Corners whose bilinear weight is exactly zero are never allowed to contribute (the reference
-// multiplies whatever it reads by 0: raytracing.cu:416-428, SURVEY note N3).
+// raytracing.cu:405-441 with s1..s4 written in terms of the minor-axis fractions (sweep_plan.cu) and
+// w_i = s_i / m_i, m_i = max(0.6, c_i sigma) (raytracing.cu:33) multiplied through by m1 m2 m3 m4.
+// Corners whose bilinear weight is exactly zero never contribute (the reference multiplies whatever it
+// reads by 0: raytracing.cu:416-428, SURVEY note N3).
 __device__ __forceinline__ double interp_coldens(double c1, double c2, double c3, double c4, double wA,
                                                  double wB, double sig, unsigned flags)
 {
@@ -69,13 +112,19 @@ __device__ __forceinline__ double interp_coldens(double c1, double c2, double c3
     c2 = (s2 != 0.0) ? c2 : 0.0;
     c3 = (s3 != 0.0) ? c3 : 0.0;
     c4 = (s4 != 0.0) ? c4 : 0.0;
-    const double w1 = s1 * weightf(c1, sig);
-    const double w2 = s2 * weightf(c2, sig);
-    const double w3 = s3 * weightf(c3, sig);
-    const double w4 = s4 * weightf(c4, sig);
-    double cdensi = (c1 * w1 + c2 * w2 + c3 * w3 + c4 * w4) / (w1 + w2 + w3 + w4);
-    if (flags & PC_DIAG3) cdensi = ASORA_SQRT3 * cdensi;
-    if (flags & PC_DIAG2) cdensi = ASORA_SQRT2 * cdensi;
+    const double m1 = fmax(0.6, c1 * sig), m2 = fmax(0.6, c2 * sig);
+    const double m3 = fmax(0.6, c3 * sig), m4 = fmax(0.6, c4 * sig);
+    double cdensi;
+    if (fmax(fmax(m1, m2), fmax(m3, m4)) < 1e90) {
+        const double m12 = m1 * m2, m34 = m3 * m4;
+        const double w1 = s1 * (m2 * m34), w2 = s2 * (m1 * m34);
+        const double w3 = s3 * (m4 * m12), w4 = s4 * (m3 * m12);
+        cdensi = fast_div(c1 * w1 + c2 * w2 + c3 * w3 + c4 * w4, w1 + w2 + w3 + w4);
+    } else {  // products would overflow: the reference's literal form
+        const double w1 = s1 / m1, w2 = s2 / m2, w3 = s3 / m3, w4 = s4 / m4;
+        cdensi = (c1 * w1 + c2 * w2 + c3 * w3 + c4 * w4) / (w1 + w2 + w3 + w4);
+    }
+    if (flags & (PC_DIAG2 | PC_DIAG3)) cdensi *= (flags & PC_DIAG3) ? ASORA_SQRT3 : ASORA_SQRT2;
     return cdensi;
 }
 
@@ -86,23 +135,27 @@ __device__ __forceinline__ int wrap(int i, int N)
     return i;
 }
 
-// Everything after the incoming column density is known: raytracing.cu:300-329.
+// Everything after the incoming column density is known: raytracing.cu:300-329 + rates.cu:16-41.
 // Returns the outgoing column density.
-__device__ __forceinline__ double finish_cell(double coldensh_in, double path_cells, double np, unsigned flags,
-                                              double nHI_p, double strength, size_t pos, const SweepParams& p)
+__device__ __forceinline__ double finish_cell(double coldensh_in, double path_cells, double inv_np, unsigned flags,
+                                              double nHI_p, double strength, size_t pos, const SweepParams& p,
+                                              const double2* __restrict__ log2_tab)
 {
-    double path, vol_ph;
-    if (flags & PC_SOURCE) {
-        path = 0.5 * p.dr;
-        vol_ph = p.dr3;
-    } else {
-        path = path_cells * p.dr;
-        vol_ph = np * p.volfac;
-    }
-    const double cdho = coldensh_in + nHI_p * path;
+    const double cdho = fma(nHI_p, path_cells * p.dr, coldensh_in);
     if ((flags & PC_RATED) && coldensh_in <= ASORA_MAX_COLDENSH) {
-        double phi = photoion_rate(strength, coldensh_in, cdho, vol_ph, p);
-        phi /= nHI_p;
+        const double tau_in = coldensh_in * p.sig;
+        const double tau_out = cdho * p.sig;
+        const double dtau = tau_out - tau_in;
+        const bool thick = fabs(dtau) > ASORA_TAU_PHOTO_LIMIT;
+        const double l_in = fast_log2(fmax(1.0e-20, tau_in), log2_tab);
+        const double l_out = fast_log2(fmax(1.0e-20, tau_out), log2_tab);
+        const double t_in = photo_lookup(p.thick, l_in, p);
+        const double t_out = photo_lookup(thick ? p.thick : p.thin, l_out, p);
+        // rates.cu:28-38: thick cells absorb T(tau_in) - T(tau_out), thin cells dtau * T_thin(tau_out)
+        const double absorbed = thick ? (t_in - t_out) : dtau * t_out;
+        const double num = (strength * (inv_np * p.inv_volfac)) * absorbed;  // prefact * ...  (rates.cu:24)
+        // raytracing.cu:324.  nHI == 0 (fully ionised input cell) divides by zero in the reference too.
+        const double phi = (nHI_p != 0.0) ? fast_div(num, nHI_p) : num / nHI_p;
         // one fire-and-forget fp64 reduction per rated (source, cell) pair: RED.E.ADD.F64 at L2
         atomicAdd(p.phi_ion + pos, phi);
     }
@@ -116,9 +169,15 @@ template <int S>
 __global__ void sweep_smem_kernel(const PlanCell* __restrict__ plan, const int* __restrict__ level_start,
                                   int nlevels, int max_level_cells, SweepParams p)
 {
-    extern __shared__ double sh_cd[];  // [2][S][max_level_cells]
+    extern __shared__ double2 sh_raw[];
+    double2* log2_tab = sh_raw;                                 // 256 entries
+    double* sh_cd = reinterpret_cast<double*>(sh_raw + 256);    // [2][S][max_level_cells]
     const int N = p.N;
     const int first = blockIdx.x * S;
+
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) log2_tab[t] = __ldg(p.log2_tab + t);
+    // the source cell "interpolates" slot 0 of the (empty) previous level with weight 1: seed it with 0
+    if (threadIdx.x < S) sh_cd[(size_t)S * max_level_cells + threadIdx.x * max_level_cells] = 0.0;
 
     int i0[S], j0[S], k0[S];
     double flux[S];
@@ -132,6 +191,7 @@ __global__ void sweep_smem_kernel(const PlanCell* __restrict__ plan, const int* 
         k0[s] = p.src_pos[3 * ns + 2];
         flux[s] = p.src_flux[ns];
     }
+    __syncthreads();
 
     for (int m = 0; m < nlevels; m++) {
         const int beg = __ldg(level_start + m), end = __ldg(level_start + m + 1);
@@ -142,7 +202,7 @@ __global__ void sweep_smem_kernel(const PlanCell* __restrict__ plan, const int* 
             const int4* q = reinterpret_cast<const int4*>(plan + e);
             const int4 r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2);
             const double wA = __hiloint2double(r0.y, r0.x), wB = __hiloint2double(r0.w, r0.z);
-            const double path = __hiloint2double(r1.y, r1.x), np = __hiloint2double(r1.w, r1.z);
+            const double path = __hiloint2double(r1.y, r1.x), inv_np = __hiloint2double(r1.w, r1.z);
             const int nb1 = r2.x & 0xffff, nb2 = (unsigned)r2.x >> 16;
             const int nb3 = r2.y & 0xffff, nb4 = (unsigned)r2.y >> 16;
             const int di = (int)(signed char)(r2.z & 0xff), dj = (int)(signed char)((r2.z >> 8) & 0xff);
@@ -154,14 +214,10 @@ __global__ void sweep_smem_kernel(const PlanCell* __restrict__ plan, const int* 
                 if (!live[s]) continue;
                 const int i = wrap(i0[s] + di, N), j = wrap(j0[s] + dj, N), k = wrap(k0[s] + dk, N);
                 const size_t pos = ((size_t)i * N + j) * N + k;
-                const double xh_av_p = __ldg(p.xh_av + pos);
-                const double nHI_p = __ldg(p.ndens + pos) * (1.0 - xh_av_p);
-                double cin = 0.0;
-                if (!(flags & PC_SOURCE)) {
-                    const double* pv = prev + s * max_level_cells;
-                    cin = interp_coldens(pv[nb1], pv[nb2], pv[nb3], pv[nb4], wA, wB, p.sig, flags);
-                }
-                const double cdho = finish_cell(cin, path, np, flags, nHI_p, flux[s], pos, p);
+                const double nHI_p = __ldg(p.nhi + pos);
+                const double* pv = prev + s * max_level_cells;
+                const double cin = interp_coldens(pv[nb1], pv[nb2], pv[nb3], pv[nb4], wA, wB, p.sig, flags);
+                const double cdho = finish_cell(cin, path, inv_np, flags, nHI_p, flux[s], pos, p, log2_tab);
                 cur[s * max_level_cells + slot] = cdho;
                 if (p.coldens_out) p.coldens_out[pos] = cdho;
             }
@@ -172,7 +228,7 @@ __global__ void sweep_smem_kernel(const PlanCell* __restrict__ plan, const int* 
 
 size_t sweep_smem_bytes(const SweepPlan& plan, int S)
 {
-    return (size_t)2 * S * plan.max_level_cells * sizeof(double);
+    return 256 * sizeof(double2) + (size_t)2 * S * plan.max_level_cells * sizeof(double);
 }
 
 template <int S>
@@ -237,6 +293,9 @@ __device__ __forceinline__ int isign1(int x) { return x >= 0 ? 1 : -1; }
 __global__ void sweep_grid_kernel(SweepParams p, int nlevels)
 {
     cg::grid_group grid = cg::this_grid();
+    __shared__ double2 log2_tab[256];
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) log2_tab[t] = __ldg(p.log2_tab + t);
+    __syncthreads();
     const int N = p.N;
     const long long nthreads = (long long)gridDim.x * blockDim.x;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -258,10 +317,9 @@ __global__ void sweep_grid_kernel(SweepParams p, int nlevels)
                     continue;
                 const int i = wrap(i0 + di, N), j = wrap(j0 + dj, N), k = wrap(k0 + dk, N);
                 const size_t pos = ((size_t)i * N + j) * N + k;
-                const double xh_av_p = __ldg(p.xh_av + pos);
-                const double nHI_p = __ldg(p.ndens + pos) * (1.0 - xh_av_p);
+                const double nHI_p = __ldg(p.nhi + pos);
                 unsigned flags = 0;
-                double cin = 0.0, path = 0.5, np = 0.0;
+                double cin = 0.0, path = 0.5, inv_np = ASORA_FOURPI;
                 if (m == 0) {
                     flags = PC_SOURCE | PC_RATED;
                 } else {
@@ -287,7 +345,7 @@ __global__ void sweep_grid_kernel(SweepParams p, int nlevels)
                     const double dc = (double)c, da = (double)a, db = (double)b;
                     const double wA = da / dc, wB = db / dc;
                     path = sqrt((da * da + db * db) / (dc * dc) + 1.0);
-                    np = (double)(ia * ia + ja * ja + ka * ka) * path;
+                    inv_np = 1.0 / ((double)(ia * ia + ja * ja + ka * ka) * path);
                     if (c == 1 && (a == 1 || b == 1)) flags |= (a == 1 && b == 1) ? PC_DIAG3 : PC_DIAG2;
                     // sphere test in the reference's own form (raytracing.cu:302-305,315)
                     const double xs = p.dr * (double)di, ys = p.dr * (double)dj, zs = p.dr * (double)dk;
@@ -301,7 +359,7 @@ __global__ void sweep_grid_kernel(SweepParams p, int nlevels)
                     const double c4 = ((1.0 - wA) * (1.0 - wB) != 0.0) ? __ldcg(slab + q4) : 0.0;
                     cin = interp_coldens(c1, c2, c3, c4, wA, wB, p.sig, flags);
                 }
-                const double cdho = finish_cell(cin, path, np, flags, nHI_p, strength, pos, p);
+                const double cdho = finish_cell(cin, path, inv_np, flags, nHI_p, strength, pos, p, log2_tab);
                 __stcg(slab + pos, cdho);
             }
             grid.sync();
@@ -328,4 +386,42 @@ cudaError_t launch_sweep_grid(const SweepParams& p, cudaStream_t stream, int* la
     void* args[] = {(void*)&pc, (void*)&nlevels};
     if (launches) *launches += 1;
     return cudaLaunchCooperativeKernel((void*)sweep_grid_kernel, dim3(sms * per_sm), dim3(block), args, 0, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// small preparation kernels
+// ---------------------------------------------------------------------------------------------------
+
+// nHI = ndens * (1 - xh_av) (raytracing.cu:275-276), once per sweep instead of once per (source, cell):
+// halves the scattered loads of the sweep.
+__global__ void prepare_nhi_kernel(const double* __restrict__ ndens, const double* __restrict__ xh_av,
+                                   double* __restrict__ nhi, int64_t ncell)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (int64_t)gridDim.x * blockDim.x)
+        nhi[i] = ndens[i] * (1.0 - xh_av[i]);
+}
+
+cudaError_t launch_prepare_nhi(const double* ndens, const double* xh_av, double* nhi, int64_t ncell, cudaStream_t stream)
+{
+    int64_t blocks = (ncell + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    prepare_nhi_kernel<<<(int)blocks, 256, 0, stream>>>(ndens, xh_av, nhi, ncell);
+    return cudaGetLastError();
+}
+
+// {T[i], T[i+1]-T[i]} pairs; the last slope is 0 (index clamp, see photo_lookup)
+__global__ void pair_table_kernel(const double* __restrict__ table, double2* __restrict__ pairs, int ntab)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ntab) {
+        const double t0 = table[i];
+        const double t1 = (i + 1 < ntab) ? table[i + 1] : t0;
+        pairs[i] = make_double2(t0, t1 - t0);
+    }
+}
+
+cudaError_t launch_pair_table(const double* table, double2* pairs, int ntab, cudaStream_t stream)
+{
+    pair_table_kernel<<<(ntab + 255) / 256, 256, 0, stream>>>(table, pairs, ntab);
+    return cudaGetLastError();
 }

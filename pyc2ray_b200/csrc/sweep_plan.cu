@@ -3,10 +3,12 @@
 // The geometry of the short-characteristics interpolation depends only on the offset of a cell from
 // its source (src/asora/raytracing.cu:370-386,397-408,444), so it is tabulated once per (N, R, dr)
 // and shared by every source: the sweep kernel then does no index arithmetic beyond the periodic
-// wrap of one cell.  Cells are grouped in Chebyshev levels (see asora_common.cuh) and ordered
-// lexicographically in (di,dj,dk) inside a level, so that consecutive threads touch consecutive k
-// (the contiguous axis of the grids, raytracing.cu:30) on four of the six faces of a level, and so
-// that the upstream slots of consecutive cells are consecutive shared-memory words.
+// wrap of one cell.  Cells are grouped in Chebyshev levels (see asora_common.cuh).  Inside a level the
+// cells that receive a rate (inside the R sphere) come first, so that whole warps skip the rate
+// arithmetic for the octahedron's corners; within each group the order is lexicographic in
+// (di,dj,dk), so that consecutive threads touch consecutive k (the contiguous axis of the grids,
+// raytracing.cu:30) on four of the six faces of a level, and the upstream slots of consecutive
+// cells are consecutive shared-memory words.
 #include "asora_common.cuh"
 
 #include <algorithm>
@@ -78,19 +80,35 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, std::string& 
     }
     const int64_t total = plan.level_start[nlevels];
     plan.cells.resize(total);
-    // pass 2: slots (rank inside the level, lexicographic enumeration order)
+    // pass 2: slots = rank inside the level, rated cells first, lexicographic inside each group
     std::vector<int32_t> slot((size_t)side * side * side, -1);
-    std::vector<int> fill(nlevels, 0);
     auto sidx = [&](int i, int j, int k) { return ((size_t)(i - lo) * side + (j - lo)) * side + (k - lo); };
-    for (int i = lo; i <= hi; i++)
-        for (int j = lo; j <= hi; j++)
-            for (int k = lo; k <= hi; k++) {
-                if (std::abs(i) + std::abs(j) + std::abs(k) > Q) continue;
-                int m = std::max(std::abs(i), std::max(std::abs(j), std::abs(k)));
-                slot[sidx(i, j, k)] = fill[m]++;
-            }
-    // pass 3: geometry
     const double R2 = R * R;
+    // Sphere test exactly as the reference kernel evaluates it (raytracing.cu:302-305,315), nvcc
+    // contracting xs*xs+ys*ys+zs*zs into DMUL,DFMA,DFMA (confirmed against the reference kernel on
+    // B200: tests/test_gpu_vs_reference_kernel.py, case r_int5).
+    auto rated = [&](int i, int j, int k) {
+        const double xs = dr * (double)i, ys = dr * (double)j, zs = dr * (double)k;
+        const double dist2 = std::fma(zs, zs, std::fma(ys, ys, xs * xs));
+        return dist2 / (dr * dr) <= R2;
+    };
+    {
+        std::vector<int> fill_rated(nlevels, 0), nrated(nlevels, 0), fill_un(nlevels, 0);
+        for (int i = lo; i <= hi; i++)
+            for (int j = lo; j <= hi; j++)
+                for (int k = lo; k <= hi; k++) {
+                    if (std::abs(i) + std::abs(j) + std::abs(k) > Q) continue;
+                    if (rated(i, j, k)) nrated[std::max(std::abs(i), std::max(std::abs(j), std::abs(k)))]++;
+                }
+        for (int i = lo; i <= hi; i++)
+            for (int j = lo; j <= hi; j++)
+                for (int k = lo; k <= hi; k++) {
+                    if (std::abs(i) + std::abs(j) + std::abs(k) > Q) continue;
+                    int m = std::max(std::abs(i), std::max(std::abs(j), std::abs(k)));
+                    slot[sidx(i, j, k)] = rated(i, j, k) ? fill_rated[m]++ : nrated[m] + fill_un[m]++;
+                }
+    }
+    // pass 3: geometry
     for (int i = lo; i <= hi; i++)
         for (int j = lo; j <= hi; j++)
             for (int k = lo; k <= hi; k++) {
@@ -105,10 +123,13 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, std::string& 
                 pc.flags = 0;
                 pc.nb[0] = pc.nb[1] = pc.nb[2] = pc.nb[3] = 0;
                 if (m == 0) {
+                    // source cell: no incoming column, path dr/2, volume dr^3 (raytracing.cu:285-294).
+                    // wA = wB = 0 makes it "interpolate" slot 0 of the previous buffer with weight 1;
+                    // the kernel seeds that slot with 0.
                     pc.flags = PC_SOURCE | PC_RATED;
                     pc.wA = pc.wB = 0.0;
-                    pc.path = 0.5;  // raytracing.cu:290
-                    pc.np = 0.0;
+                    pc.path = 0.5;
+                    pc.inv_np = ASORA_FOURPI;
                 } else {
                     const int si = sign1(i), sj = sign1(j), sk = sign1(k);
                     const int im = i - si, jm = j - sj, km = k - sk;
@@ -141,13 +162,9 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, std::string& 
                     const double da = a, db = b, dc = c;
                     pc.path = std::sqrt((da * da + db * db) / (dc * dc) + 1.0);  // raytracing.cu:444
                     const int n = ia * ia + ja * ja + ka * ka;
-                    pc.np = (double)n * pc.path;
+                    pc.inv_np = 1.0 / ((double)n * pc.path);
                     if (c == 1 && (a == 1 || b == 1)) pc.flags |= (a == 1 && b == 1) ? PC_DIAG3 : PC_DIAG2;
-                    // Sphere test exactly as the reference kernel evaluates it (raytracing.cu:302-305,315),
-                    // nvcc contracting xs*xs+ys*ys+zs*zs into DMUL,DFMA,DFMA.
-                    const double xs = dr * (double)i, ys = dr * (double)j, zs = dr * (double)k;
-                    const double dist2 = std::fma(zs, zs, std::fma(ys, ys, xs * xs));
-                    if (dist2 / (dr * dr) <= R2) pc.flags |= PC_RATED;
+                    if (rated(i, j, k)) pc.flags |= PC_RATED;
                     // upstream slots; zero-weight corners may fall outside the plan -> slot 0, weight 0
                     const double s[4] = {pc.wA * pc.wB, pc.wB * (1.0 - pc.wA), pc.wA * (1.0 - pc.wB),
                                          (1.0 - pc.wA) * (1.0 - pc.wB)};
