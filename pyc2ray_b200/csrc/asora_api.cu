@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <utility>
 #include <string>
 
 namespace {
@@ -29,8 +31,10 @@ struct Context {
     int ntab = 0;
     double* nhi = nullptr;      // ndens * (1 - xh_av), rebuilt before every sweep
     double2* log2_tab = nullptr;
-    int* src_pos = nullptr;
+    int* src_pos = nullptr;      // as uploaded (positions reduced modulo N)
     double* src_flux = nullptr;
+    int* src_pos_sorted = nullptr;   // the same sources in Morton order of their cells: consecutive CTAs
+    double* src_flux_sorted = nullptr;  // then sweep neighbouring regions and share ndens/phi lines in L2
     int nsrc = 0;
     SweepPlan plan;
     // chemistry scratch
@@ -42,7 +46,7 @@ struct Context {
     int64_t chem_stage_n = 0;
     // stats of the last sweep
     int variant_forced = 0;
-    int tune_S = 0, tune_block = 0;
+    int tune_S = 0, tune_block = 0, tune_regs = 0;
     int last_launches_prep = 0;
     int last_variant = 0, last_launches = 0, last_qmax = 0, last_levels = 0;
     int64_t last_updates = 0;
@@ -140,8 +144,10 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     p.phi_ion = g.buf[ASORA_BUF_PHI_ION];
     p.thin = g.thin;
     p.thick = g.thick;
-    p.src_pos = g.src_pos;
-    p.src_flux = g.src_flux;
+    // a sweep over the whole list may take the sources in any order (phi_ion is a sum)
+    const bool whole = (begin == 0 && count == g.nsrc && g.src_pos_sorted != nullptr);
+    p.src_pos = whole ? g.src_pos_sorted : g.src_pos;
+    p.src_flux = whole ? g.src_flux_sorted : g.src_flux;
     p.src_begin = begin;
     p.src_count = count;
     p.coldens_out = coldens_grid;
@@ -188,7 +194,7 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     CK(cudaEventRecord(g.ev0, g.stream));
     if (variant == 1) {
         g.last_levels = g.plan.nlevels;
-        cudaError_t e = launch_sweep_smem(g.plan, p, S, block, g.stream, &g.last_launches);
+        cudaError_t e = launch_sweep_smem(g.plan, p, S, block, g.tune_regs, g.stream, &g.last_launches);
         if (e != cudaSuccess) return fail_cuda("sweep_smem_kernel launch", e);
     } else {
         if (!p.coldens_out) {
@@ -262,6 +268,10 @@ int asora_device_close(void)
     g.log2_tab = nullptr;
     if (g.src_pos) cudaFree(g.src_pos);
     if (g.src_flux) cudaFree(g.src_flux);
+    if (g.src_pos_sorted) cudaFree(g.src_pos_sorted);
+    if (g.src_flux_sorted) cudaFree(g.src_flux_sorted);
+    g.src_pos_sorted = nullptr;
+    g.src_flux_sorted = nullptr;
     if (g.chem_partials) cudaFree(g.chem_partials);
     if (g.chem_iparts) cudaFree(g.chem_iparts);
     for (int i = 0; i < 6; i++) {
@@ -321,8 +331,10 @@ int asora_source_data_to_device(const int32_t* pos, const double* flux, int NumS
     if (NumSrc < 0 || (NumSrc > 0 && (!pos || !flux))) return fail("source_data_to_device: bad arguments");
     if (g.src_pos) cudaFree(g.src_pos);
     if (g.src_flux) cudaFree(g.src_flux);
-    g.src_pos = nullptr;
-    g.src_flux = nullptr;
+    if (g.src_pos_sorted) cudaFree(g.src_pos_sorted);
+    if (g.src_flux_sorted) cudaFree(g.src_flux_sorted);
+    g.src_pos = g.src_pos_sorted = nullptr;
+    g.src_flux = g.src_flux_sorted = nullptr;
     g.nsrc = 0;
     if (NumSrc == 0) return 0;
     // The sweep is periodic (modulo_gpu, raytracing.cu:270-272): reduce positions to [0,N) once here.
@@ -332,6 +344,33 @@ int asora_source_data_to_device(const int32_t* pos, const double* flux, int NumS
     CK(cudaMalloc(&g.src_flux, sizeof(double) * (size_t)NumSrc));
     CK(cudaMemcpyAsync(g.src_pos, wrapped.data(), sizeof(int32_t) * 3 * (size_t)NumSrc, cudaMemcpyHostToDevice, g.stream));
     CK(cudaMemcpyAsync(g.src_flux, flux, sizeof(double) * (size_t)NumSrc, cudaMemcpyHostToDevice, g.stream));
+    // Morton-ordered copy
+    std::vector<std::pair<uint64_t, int>> key((size_t)NumSrc);
+    auto spread = [](uint64_t v) {  // 21 bits -> every third bit
+        v &= 0x1fffff;
+        v = (v | v << 32) & 0x1f00000000ffffULL;
+        v = (v | v << 16) & 0x1f0000ff0000ffULL;
+        v = (v | v << 8) & 0x100f00f00f00f00fULL;
+        v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
+        v = (v | v << 2) & 0x1249249249249249ULL;
+        return v;
+    };
+    for (int n = 0; n < NumSrc; n++)
+        key[n] = {spread(wrapped[3 * n]) << 2 | spread(wrapped[3 * n + 1]) << 1 | spread(wrapped[3 * n + 2]), n};
+    std::sort(key.begin(), key.end());
+    std::vector<int32_t> spos(3 * (size_t)NumSrc);
+    std::vector<double> sflux((size_t)NumSrc);
+    for (int n = 0; n < NumSrc; n++) {
+        const int o = key[n].second;
+        spos[3 * n] = wrapped[3 * o];
+        spos[3 * n + 1] = wrapped[3 * o + 1];
+        spos[3 * n + 2] = wrapped[3 * o + 2];
+        sflux[n] = flux[o];
+    }
+    CK(cudaMalloc(&g.src_pos_sorted, sizeof(int32_t) * 3 * (size_t)NumSrc));
+    CK(cudaMalloc(&g.src_flux_sorted, sizeof(double) * (size_t)NumSrc));
+    CK(cudaMemcpyAsync(g.src_pos_sorted, spos.data(), sizeof(int32_t) * 3 * (size_t)NumSrc, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.src_flux_sorted, sflux.data(), sizeof(double) * (size_t)NumSrc, cudaMemcpyHostToDevice, g.stream));
     CK(cudaStreamSynchronize(g.stream));
     g.nsrc = NumSrc;
     return 0;
@@ -486,6 +525,9 @@ int asora_set_sweep_variant(int variant)
 
 int asora_set_tuning(int sources_per_cta, int block_threads)
 {
+    // bit 16 of block_threads selects the relaxed register mode (profiling knob)
+    g.tune_regs = (block_threads >> 16) & 1;
+    block_threads &= 0xffff;
     if (!(sources_per_cta == 0 || sources_per_cta == 1 || sources_per_cta == 2 || sources_per_cta == 4))
         return fail("set_tuning: sources_per_cta must be 0, 1, 2 or 4");
     if (block_threads < 0 || block_threads > 1024 || block_threads % 32) return fail("set_tuning: bad block size");

@@ -90,7 +90,7 @@ void free_sweep_plan(SweepPlan& plan);
 // launchers implemented in sweep_kernels.cu
 size_t sweep_smem_bytes(const SweepPlan& plan, int sources_per_cta);
 cudaError_t launch_sweep_smem(const SweepPlan& plan, const SweepParams& p, int sources_per_cta, int block,
-                              cudaStream_t stream, int* launches);
+                              int regs_mode, cudaStream_t stream, int* launches);
 cudaError_t launch_sweep_grid(const SweepParams& p, cudaStream_t stream, int* launches, int* levels);
 
 cudaError_t launch_prepare_nhi(const double* ndens, const double* xh_av, double* nhi, int64_t ncell, cudaStream_t stream);

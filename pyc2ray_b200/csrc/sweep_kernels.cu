@@ -165,8 +165,49 @@ __device__ __forceinline__ double finish_cell(double coldensh_in, double path_ce
 // ---------------------------------------------------------------------------------------------------
 // variant 1: shared-memory level sweep, S sources per CTA
 // ---------------------------------------------------------------------------------------------------
+// One plan cell with its per-source grid positions and neutral densities already fetched.
 template <int S>
-__global__ void sweep_smem_kernel(const PlanCell* __restrict__ plan, const int* __restrict__ level_start,
+struct Fetched {
+    double wA, wB, path, inv_np;
+    int nb1, nb2, nb3, nb4;
+    unsigned flags;
+    unsigned pos[S];
+    double nhi[S];
+};
+
+template <int S>
+__device__ __forceinline__ void fetch_cell(Fetched<S>& f, const PlanCell* __restrict__ plan, int e, const int (&i0)[S],
+                                           const int (&j0)[S], const int (&k0)[S], int N, const double* __restrict__ nhi)
+{
+    // plan cell: three 16-byte read-only loads, shared by the S sources
+    const int4* q = reinterpret_cast<const int4*>(plan + e);
+    const int4 r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2);
+    f.wA = __hiloint2double(r0.y, r0.x);
+    f.wB = __hiloint2double(r0.w, r0.z);
+    f.path = __hiloint2double(r1.y, r1.x);
+    f.inv_np = __hiloint2double(r1.w, r1.z);
+    f.nb1 = r2.x & 0xffff;
+    f.nb2 = (unsigned)r2.x >> 16;
+    f.nb3 = r2.y & 0xffff;
+    f.nb4 = (unsigned)r2.y >> 16;
+    const int di = (int)(signed char)(r2.z & 0xff), dj = (int)(signed char)((r2.z >> 8) & 0xff);
+    const int dk = (int)(signed char)((r2.z >> 16) & 0xff);
+    f.flags = ((unsigned)r2.z >> 24) & 0xffu;
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        const int i = wrap(i0[s] + di, N), j = wrap(j0[s] + dj, N), k = wrap(k0[s] + dk, N);
+        f.pos[s] = ((unsigned)i * N + j) * N + k;  // N <= 1600: fits 32 bits
+        f.nhi[s] = __ldg(nhi + f.pos[s]);
+    }
+}
+
+// One CTA per S sources.  Per level: every thread updates its cells (plan entry + neutral density from
+// global memory, four upstream column densities from the previous level's shared-memory buffer), then a
+// CTA barrier hands the level over.  (An explicitly software-pipelined version that prefetched the next
+// cell across the barrier was measured 30 % slower on B200 -- register pressure -- and dropped.)
+template <int S, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+sweep_smem_kernel(const PlanCell* __restrict__ plan, const int* __restrict__ level_start,
                                   int nlevels, int max_level_cells, SweepParams p)
 {
     extern __shared__ double2 sh_raw[];
@@ -175,7 +216,7 @@ __global__ void sweep_smem_kernel(const PlanCell* __restrict__ plan, const int* 
     const int N = p.N;
     const int first = blockIdx.x * S;
 
-    for (int t = threadIdx.x; t < 256; t += blockDim.x) log2_tab[t] = __ldg(p.log2_tab + t);
+    for (int t = threadIdx.x; t < 256; t += BLOCK) log2_tab[t] = __ldg(p.log2_tab + t);
     // the source cell "interpolates" slot 0 of the (empty) previous level with weight 1: seed it with 0
     if (threadIdx.x < S) sh_cd[(size_t)S * max_level_cells + threadIdx.x * max_level_cells] = 0.0;
 
@@ -197,29 +238,18 @@ __global__ void sweep_smem_kernel(const PlanCell* __restrict__ plan, const int* 
         const int beg = __ldg(level_start + m), end = __ldg(level_start + m + 1);
         double* cur = sh_cd + (size_t)(m & 1) * S * max_level_cells;
         const double* prev = sh_cd + (size_t)((m & 1) ^ 1) * S * max_level_cells;
-        for (int e = beg + threadIdx.x; e < end; e += blockDim.x) {
-            // plan cell: three 16-byte read-only loads, shared by the S sources
-            const int4* q = reinterpret_cast<const int4*>(plan + e);
-            const int4 r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2);
-            const double wA = __hiloint2double(r0.y, r0.x), wB = __hiloint2double(r0.w, r0.z);
-            const double path = __hiloint2double(r1.y, r1.x), inv_np = __hiloint2double(r1.w, r1.z);
-            const int nb1 = r2.x & 0xffff, nb2 = (unsigned)r2.x >> 16;
-            const int nb3 = r2.y & 0xffff, nb4 = (unsigned)r2.y >> 16;
-            const int di = (int)(signed char)(r2.z & 0xff), dj = (int)(signed char)((r2.z >> 8) & 0xff);
-            const int dk = (int)(signed char)((r2.z >> 16) & 0xff);
-            const unsigned flags = ((unsigned)r2.z >> 24) & 0xffu;
+        for (int e = beg + threadIdx.x; e < end; e += BLOCK) {
+            Fetched<S> c;
+            fetch_cell<S>(c, plan, e, i0, j0, k0, N, p.nhi);
             const int slot = e - beg;
 #pragma unroll
             for (int s = 0; s < S; s++) {
                 if (!live[s]) continue;
-                const int i = wrap(i0[s] + di, N), j = wrap(j0[s] + dj, N), k = wrap(k0[s] + dk, N);
-                const size_t pos = ((size_t)i * N + j) * N + k;
-                const double nHI_p = __ldg(p.nhi + pos);
                 const double* pv = prev + s * max_level_cells;
-                const double cin = interp_coldens(pv[nb1], pv[nb2], pv[nb3], pv[nb4], wA, wB, p.sig, flags);
-                const double cdho = finish_cell(cin, path, inv_np, flags, nHI_p, flux[s], pos, p, log2_tab);
+                const double cin = interp_coldens(pv[c.nb1], pv[c.nb2], pv[c.nb3], pv[c.nb4], c.wA, c.wB, p.sig, c.flags);
+                const double cdho = finish_cell(cin, c.path, c.inv_np, c.flags, c.nhi[s], flux[s], c.pos[s], p, log2_tab);
                 cur[s * max_level_cells + slot] = cdho;
-                if (p.coldens_out) p.coldens_out[pos] = cdho;
+                if (p.coldens_out) p.coldens_out[c.pos[s]] = cdho;
             }
         }
         __syncthreads();
@@ -231,29 +261,40 @@ size_t sweep_smem_bytes(const SweepPlan& plan, int S)
     return 256 * sizeof(double2) + (size_t)2 * S * plan.max_level_cells * sizeof(double);
 }
 
-template <int S>
-static cudaError_t launch_smem_t(const SweepPlan& plan, const SweepParams& p, int block, cudaStream_t stream)
+template <int S, int BLOCK, int MINB>
+static cudaError_t launch_smem_t(const SweepPlan& plan, const SweepParams& p, cudaStream_t stream)
 {
     const size_t smem = sweep_smem_bytes(plan, S);
-    cudaError_t e = cudaFuncSetAttribute(sweep_smem_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(sweep_smem_kernel<S, BLOCK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = (p.src_count + S - 1) / S;
-    sweep_smem_kernel<S><<<grid, block, smem, stream>>>(plan.d_cells, plan.d_level_start, plan.nlevels,
-                                                        plan.max_level_cells, p);
+    sweep_smem_kernel<S, BLOCK, MINB><<<grid, BLOCK, smem, stream>>>(plan.d_cells, plan.d_level_start, plan.nlevels,
+                                                                   plan.max_level_cells, p);
     return cudaGetLastError();
 }
 
-cudaError_t launch_sweep_smem(const SweepPlan& plan, const SweepParams& p, int S, int block, cudaStream_t stream,
-                              int* launches)
+// `block` in {128,256,512,1024}; `regs_mode` 0 caps registers at 64/thread (full occupancy), 1 allows
+// ~128/thread (half occupancy, no spills of the prefetch registers).
+cudaError_t launch_sweep_smem(const SweepPlan& plan, const SweepParams& p, int S, int block, int regs_mode,
+                              cudaStream_t stream, int* launches)
 {
     if (p.src_count <= 0) return cudaSuccess;
     if (launches) *launches += 1;
-    switch (S) {
-        case 1: return launch_smem_t<1>(plan, p, block, stream);
-        case 2: return launch_smem_t<2>(plan, p, block, stream);
-        case 4: return launch_smem_t<4>(plan, p, block, stream);
-        default: return cudaErrorInvalidValue;
-    }
+#define ASORA_CASE(SS, BB, M0, M1)                                                       \
+    if (S == SS && block == BB)                                                          \
+        return regs_mode ? launch_smem_t<SS, BB, M1>(plan, p, stream) : launch_smem_t<SS, BB, M0>(plan, p, stream);
+    ASORA_CASE(1, 128, 8, 4)
+    ASORA_CASE(1, 256, 4, 2)
+    ASORA_CASE(1, 512, 2, 1)
+    ASORA_CASE(1, 1024, 1, 1)
+    ASORA_CASE(2, 128, 8, 4)
+    ASORA_CASE(2, 256, 4, 2)
+    ASORA_CASE(2, 512, 2, 1)
+    ASORA_CASE(2, 1024, 1, 1)
+    ASORA_CASE(4, 256, 4, 2)
+    ASORA_CASE(4, 512, 2, 1)
+#undef ASORA_CASE
+    return cudaErrorInvalidValue;
 }
 
 // ---------------------------------------------------------------------------------------------------
