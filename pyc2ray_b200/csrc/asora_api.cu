@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <algorithm>
 #include <utility>
 #include <string>
@@ -135,6 +136,9 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     // rates.cu:77-78: index = 1 + (log10(tau) - minlogtau)/dlogtau = lut_a + lut_b * log2(tau)
     p.lut_b = 0.30102999566398119521 / dlogtau;
     p.lut_a = 1.0 - minlogtau / dlogtau;
+    // rates.cu:77-78 clamps: tau >= 1e-20, 0 <= index <= NumTau  <=>  tau_lo <= tau <= tau_hi
+    p.tau_lo = std::max(1.0e-20, std::pow(10.0, minlogtau - dlogtau));
+    p.tau_hi = std::pow(10.0, minlogtau + ((double)NumTau - 1.0) * dlogtau);
     p.minlogtau = minlogtau;
     p.dlogtau = dlogtau;
     p.NumTau = NumTau;

@@ -37,7 +37,7 @@ struct __align__(16) PlanCell {
     double inv_np;   // 1 / ((di^2+dj^2+dk^2) * path): 1/vol_ph = inv_np / (4 pi dr^3) (raytracing.cu:300-307);
                      // 4 pi for the source cell, whose volume is dr^3 (raytracing.cu:292)
     uint16_t nb[4];  // slots, in the previous level, of the 4 upstream cells c1..c4
-    int8_t d[3];     // offset from the source
+    uint8_t d[3];    // offset from the source, biased by -plan.lo (index into the per-source wrap tables)
     uint8_t flags;
     uint32_t pad;
 };
@@ -49,6 +49,7 @@ struct SweepPlan {
     int q_max = 0;
     int nlevels = 0;
     int max_level_cells = 0;
+    int lo = 0, side = 0;              // offsets span [lo, lo+side) on every axis
     int64_t ncells = 0;                // cells per source
     std::vector<int> level_start;      // nlevels+1
     std::vector<PlanCell> cells;       // level-major, lexicographic (di,dj,dk) inside a level
@@ -66,6 +67,7 @@ struct SweepParams {
     double sig, dr;
     double inv_volfac;        // 1 / (4 pi dr^3)
     double lut_a, lut_b;      // table index = lut_a + lut_b * log2(tau)  (rates.cu:77-78)
+    double tau_lo, tau_hi;    // optical depths at which that index reaches 0 (>= 1e-20) and NumTau
     double minlogtau, dlogtau;
     int NumTau;               // index clamp as passed by the caller (rates.cu:78-79)
     int ntab;                 // uploaded table length

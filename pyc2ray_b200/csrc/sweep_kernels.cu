@@ -55,6 +55,17 @@ __device__ __forceinline__ double fast_div(double a, double b)
     return fma(fma(-b, q, a), r, q);
 }
 
+// Polynomial coefficients live in the constant bank so that DFMA reads them as c[][] operands instead of
+// materialising each 64-bit immediate with two UMOVs (6.7 % of the issued instructions in r01b).
+// log2(1+r) = r * (K[0] + K[1] r + ... + K[5] r^5), K[k] = (-1)^k / ((k+1) ln 2)
+__constant__ double kLog2Poly[6] = {1.44269504088896341, -0.72134752044448170, 0.48089834696298783,
+                                    -0.36067376022224085, 0.28853900817779268, -0.24044917348149391};
+
+// max / min for ordinary (non-NaN) operands: one DSETP and two FSELs.  fmax()/fmin() cost 6-8
+// instructions each on sm_100 because of their NaN rules.
+__device__ __forceinline__ double dmax(double a, double b) { return (a > b) ? a : b; }
+__device__ __forceinline__ double dmin(double a, double b) { return (a < b) ? a : b; }
+
 // log2(x), x normal and positive.  tab[j] = {1/c_j, log2 c_j} for the 256 mantissa bins of [1,2).
 __device__ __forceinline__ double fast_log2(double x, const double2* __restrict__ tab)
 {
@@ -63,12 +74,11 @@ __device__ __forceinline__ double fast_log2(double x, const double2* __restrict_
     const double2 t = tab[(hi >> 12) & 0xff];
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
     const double r = fma(m, t.x, -1.0);  // |r| <= 2^-9
-    // log2(1+r) = r * (c1 + c2 r + ... + c6 r^5), c_k = (-1)^(k+1) / (k ln 2)
-    double p = fma(r, -0.24044917348149391, 0.28853900817779268);
-    p = fma(r, p, -0.36067376022224085);
-    p = fma(r, p, 0.48089834696298783);
-    p = fma(r, p, -0.72134752044448170);
-    p = fma(r, p, 1.44269504088896341);
+    double p = fma(r, kLog2Poly[5], kLog2Poly[4]);
+    p = fma(r, p, kLog2Poly[3]);
+    p = fma(r, p, kLog2Poly[2]);
+    p = fma(r, p, kLog2Poly[1]);
+    p = fma(r, p, kLog2Poly[0]);
     return fma(r, p, (double)e + t.y);
 }
 
@@ -86,15 +96,19 @@ void host_log2_table(double* tab512)
 // per-cell arithmetic
 // ---------------------------------------------------------------------------------------------------
 
-// rates.cu:70-83 with index = lut_a + lut_b*log2(tau).  `ntab` additionally clamps to the uploaded
-// table length (reference bug N6: Python callers pass NumTau = table length, which lets i1 reach one
-// element past the table); the pair table's last slope is 0, which is the same clamp.
-__device__ __forceinline__ double photo_lookup(const double2* __restrict__ pairs, double log2tau, const SweepParams& p)
+// rates.cu:70-83.  The reference clamps tau from below at 1e-20 and the table index to [0, NumTau];
+// here tau itself is clamped to [tau_lo, tau_hi], the optical depths at which the index reaches those
+// bounds (tau_lo >= 1e-20), so index = lut_a + lut_b*log2(tau) needs no further clamping beyond the
+// integer guard against the uploaded table length (reference bug N6: Python callers pass NumTau =
+// table length, which lets i1 reach one element past the table; the pair table's last slope is 0).
+__device__ __forceinline__ double photo_lookup(const double2* __restrict__ pairs, double tau, const SweepParams& p,
+                                               const double2* __restrict__ log2_tab)
 {
-    const double real_i = fmin((double)p.NumTau, fmax(0.0, fma(p.lut_b, log2tau, p.lut_a)));
+    const double t_c = dmin(dmax(tau, p.tau_lo), p.tau_hi);
+    const double real_i = fma(p.lut_b, fast_log2(t_c, log2_tab), p.lut_a);
     int i0 = (int)real_i;
     const double residual = real_i - (double)i0;
-    i0 = min(i0, p.ntab - 1);
+    i0 = max(0, min(i0, p.ntab - 1));
     const double2 t = __ldg(pairs + i0);
     return fma(residual, t.y, t.x);
 }
@@ -102,26 +116,31 @@ __device__ __forceinline__ double photo_lookup(const double2* __restrict__ pairs
 // raytracing.cu:405-441 with s1..s4 written in terms of the minor-axis fractions (sweep_plan.cu) and
 // w_i = s_i / m_i, m_i = max(0.6, c_i sigma) (raytracing.cu:33) multiplied through by m1 m2 m3 m4.
 // Corners whose bilinear weight is exactly zero never contribute (the reference multiplies whatever it
-// reads by 0: raytracing.cu:416-428, SURVEY note N3).
+// reads by 0: raytracing.cu:416-428, SURVEY note N3).  MASK: the caller may have read stale memory
+// for those corners, so force them to 0; the plan-driven sweep instead points them at a live slot.
+template <bool MASK>
 __device__ __forceinline__ double interp_coldens(double c1, double c2, double c3, double c4, double wA,
                                                  double wB, double sig, unsigned flags)
 {
     const double uA = 1.0 - wA, uB = 1.0 - wB;
     const double s1 = wA * wB, s2 = wB * uA, s3 = wA * uB, s4 = uA * uB;
-    c1 = (s1 != 0.0) ? c1 : 0.0;
-    c2 = (s2 != 0.0) ? c2 : 0.0;
-    c3 = (s3 != 0.0) ? c3 : 0.0;
-    c4 = (s4 != 0.0) ? c4 : 0.0;
-    const double m1 = fmax(0.6, c1 * sig), m2 = fmax(0.6, c2 * sig);
-    const double m3 = fmax(0.6, c3 * sig), m4 = fmax(0.6, c4 * sig);
+    if (MASK) {
+        c1 = (s1 != 0.0) ? c1 : 0.0;
+        c2 = (s2 != 0.0) ? c2 : 0.0;
+        c3 = (s3 != 0.0) ? c3 : 0.0;
+        c4 = (s4 != 0.0) ? c4 : 0.0;
+    }
+    const double m1 = dmax(c1 * sig, 0.6), m2 = dmax(c2 * sig, 0.6);
+    const double m3 = dmax(c3 * sig, 0.6), m4 = dmax(c4 * sig, 0.6);
+    const double m12 = m1 * m2, m34 = m3 * m4;
+    double w1 = s1 * (m2 * m34), w2 = s2 * (m1 * m34);
+    double w3 = s3 * (m4 * m12), w4 = s4 * (m3 * m12);
+    double den = (w1 + w2) + (w3 + w4);
     double cdensi;
-    if (fmax(fmax(m1, m2), fmax(m3, m4)) < 1e90) {
-        const double m12 = m1 * m2, m34 = m3 * m4;
-        const double w1 = s1 * (m2 * m34), w2 = s2 * (m1 * m34);
-        const double w3 = s3 * (m4 * m12), w4 = s4 * (m3 * m12);
-        cdensi = fast_div(c1 * w1 + c2 * w2 + c3 * w3 + c4 * w4, w1 + w2 + w3 + w4);
-    } else {  // products would overflow: the reference's literal form
-        const double w1 = s1 / m1, w2 = s2 / m2, w3 = s3 / m3, w4 = s4 / m4;
+    if (den < 1e300) {
+        cdensi = fast_div(fma(c1, w1, c2 * w2) + fma(c3, w3, c4 * w4), den);
+    } else {  // the products overflowed (column densities beyond 1e90): the reference's literal form
+        w1 = s1 / m1, w2 = s2 / m2, w3 = s3 / m3, w4 = s4 / m4;
         cdensi = (c1 * w1 + c2 * w2 + c3 * w3 + c4 * w4) / (w1 + w2 + w3 + w4);
     }
     if (flags & (PC_DIAG2 | PC_DIAG3)) cdensi *= (flags & PC_DIAG3) ? ASORA_SQRT3 : ASORA_SQRT2;
@@ -147,10 +166,8 @@ __device__ __forceinline__ double finish_cell(double coldensh_in, double path_ce
         const double tau_out = cdho * p.sig;
         const double dtau = tau_out - tau_in;
         const bool thick = fabs(dtau) > ASORA_TAU_PHOTO_LIMIT;
-        const double l_in = fast_log2(fmax(1.0e-20, tau_in), log2_tab);
-        const double l_out = fast_log2(fmax(1.0e-20, tau_out), log2_tab);
-        const double t_in = photo_lookup(p.thick, l_in, p);
-        const double t_out = photo_lookup(thick ? p.thick : p.thin, l_out, p);
+        const double t_in = photo_lookup(p.thick, tau_in, p, log2_tab);
+        const double t_out = photo_lookup(thick ? p.thick : p.thin, tau_out, p, log2_tab);
         // rates.cu:28-38: thick cells absorb T(tau_in) - T(tau_out), thin cells dtau * T_thin(tau_out)
         const double absorbed = thick ? (t_in - t_out) : dtau * t_out;
         const double num = (strength * (inv_np * p.inv_volfac)) * absorbed;  // prefact * ...  (rates.cu:24)
@@ -175,9 +192,13 @@ struct Fetched {
     double nhi[S];
 };
 
+// wrapX/Y/Z: per-source shared-memory tables, indexed by the biased offset, holding the periodic
+// cell coordinate already multiplied by its stride (N*N, N, 1): one LDS per axis replaces the
+// add / sign-fix / compare / select chain of modulo_gpu (raytracing.cu:24,270-272).
 template <int S>
-__device__ __forceinline__ void fetch_cell(Fetched<S>& f, const PlanCell* __restrict__ plan, int e, const int (&i0)[S],
-                                           const int (&j0)[S], const int (&k0)[S], int N, const double* __restrict__ nhi)
+__device__ __forceinline__ void fetch_cell(Fetched<S>& f, const PlanCell* __restrict__ plan, int e,
+                                           const unsigned* __restrict__ wrap_tab, int side,
+                                           const double* __restrict__ nhi)
 {
     // plan cell: three 16-byte read-only loads, shared by the S sources
     const int4* q = reinterpret_cast<const int4*>(plan + e);
@@ -190,13 +211,12 @@ __device__ __forceinline__ void fetch_cell(Fetched<S>& f, const PlanCell* __rest
     f.nb2 = (unsigned)r2.x >> 16;
     f.nb3 = r2.y & 0xffff;
     f.nb4 = (unsigned)r2.y >> 16;
-    const int di = (int)(signed char)(r2.z & 0xff), dj = (int)(signed char)((r2.z >> 8) & 0xff);
-    const int dk = (int)(signed char)((r2.z >> 16) & 0xff);
+    const unsigned di = r2.z & 0xff, dj = (r2.z >> 8) & 0xff, dk = (r2.z >> 16) & 0xff;
     f.flags = ((unsigned)r2.z >> 24) & 0xffu;
 #pragma unroll
     for (int s = 0; s < S; s++) {
-        const int i = wrap(i0[s] + di, N), j = wrap(j0[s] + dj, N), k = wrap(k0[s] + dk, N);
-        f.pos[s] = ((unsigned)i * N + j) * N + k;  // N <= 1600: fits 32 bits
+        const unsigned* w = wrap_tab + 3 * s * side;
+        f.pos[s] = w[di] + w[side + dj] + w[2 * side + dk];  // N <= 1600: fits 32 bits
         f.nhi[s] = __ldg(nhi + f.pos[s]);
     }
 }
@@ -208,11 +228,12 @@ __device__ __forceinline__ void fetch_cell(Fetched<S>& f, const PlanCell* __rest
 template <int S, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
 sweep_smem_kernel(const PlanCell* __restrict__ plan, const int* __restrict__ level_start,
-                                  int nlevels, int max_level_cells, SweepParams p)
+                                  int nlevels, int max_level_cells, int lo, int side, SweepParams p)
 {
     extern __shared__ double2 sh_raw[];
     double2* log2_tab = sh_raw;                                 // 256 entries
     double* sh_cd = reinterpret_cast<double*>(sh_raw + 256);    // [2][S][max_level_cells]
+    unsigned* wrap_tab = reinterpret_cast<unsigned*>(sh_cd + (size_t)2 * S * max_level_cells);  // [S][3][side]
     const int N = p.N;
     const int first = blockIdx.x * S;
 
@@ -232,6 +253,14 @@ sweep_smem_kernel(const PlanCell* __restrict__ plan, const int* __restrict__ lev
         k0[s] = p.src_pos[3 * ns + 2];
         flux[s] = p.src_flux[ns];
     }
+#pragma unroll
+    for (int s = 0; s < S; s++)
+        for (int t = threadIdx.x; t < 3 * side; t += BLOCK) {
+            const int axis = t / side, d = t - axis * side + lo;
+            const int c0 = axis == 0 ? i0[s] : (axis == 1 ? j0[s] : k0[s]);
+            const unsigned stride = axis == 0 ? (unsigned)N * N : (axis == 1 ? (unsigned)N : 1u);
+            wrap_tab[3 * s * side + t] = (unsigned)wrap(c0 + d, N) * stride;
+        }
     __syncthreads();
 
     for (int m = 0; m < nlevels; m++) {
@@ -240,13 +269,13 @@ sweep_smem_kernel(const PlanCell* __restrict__ plan, const int* __restrict__ lev
         const double* prev = sh_cd + (size_t)((m & 1) ^ 1) * S * max_level_cells;
         for (int e = beg + threadIdx.x; e < end; e += BLOCK) {
             Fetched<S> c;
-            fetch_cell<S>(c, plan, e, i0, j0, k0, N, p.nhi);
+            fetch_cell<S>(c, plan, e, wrap_tab, side, p.nhi);
             const int slot = e - beg;
 #pragma unroll
             for (int s = 0; s < S; s++) {
                 if (!live[s]) continue;
                 const double* pv = prev + s * max_level_cells;
-                const double cin = interp_coldens(pv[c.nb1], pv[c.nb2], pv[c.nb3], pv[c.nb4], c.wA, c.wB, p.sig, c.flags);
+                const double cin = interp_coldens<false>(pv[c.nb1], pv[c.nb2], pv[c.nb3], pv[c.nb4], c.wA, c.wB, p.sig, c.flags);
                 const double cdho = finish_cell(cin, c.path, c.inv_np, c.flags, c.nhi[s], flux[s], c.pos[s], p, log2_tab);
                 cur[s * max_level_cells + slot] = cdho;
                 if (p.coldens_out) p.coldens_out[c.pos[s]] = cdho;
@@ -258,7 +287,8 @@ sweep_smem_kernel(const PlanCell* __restrict__ plan, const int* __restrict__ lev
 
 size_t sweep_smem_bytes(const SweepPlan& plan, int S)
 {
-    return 256 * sizeof(double2) + (size_t)2 * S * plan.max_level_cells * sizeof(double);
+    return 256 * sizeof(double2) + (size_t)2 * S * plan.max_level_cells * sizeof(double) +
+           (size_t)3 * S * plan.side * sizeof(unsigned);
 }
 
 template <int S, int BLOCK, int MINB>
@@ -269,7 +299,7 @@ static cudaError_t launch_smem_t(const SweepPlan& plan, const SweepParams& p, cu
     if (e != cudaSuccess) return e;
     const int grid = (p.src_count + S - 1) / S;
     sweep_smem_kernel<S, BLOCK, MINB><<<grid, BLOCK, smem, stream>>>(plan.d_cells, plan.d_level_start, plan.nlevels,
-                                                                   plan.max_level_cells, p);
+                                                                   plan.max_level_cells, plan.lo, plan.side, p);
     return cudaGetLastError();
 }
 
@@ -398,7 +428,7 @@ __global__ void sweep_grid_kernel(SweepParams p, int nlevels)
                     const double c2 = (wB * (1.0 - wA) != 0.0) ? __ldcg(slab + q2) : 0.0;
                     const double c3 = (wA * (1.0 - wB) != 0.0) ? __ldcg(slab + q3) : 0.0;
                     const double c4 = ((1.0 - wA) * (1.0 - wB) != 0.0) ? __ldcg(slab + q4) : 0.0;
-                    cin = interp_coldens(c1, c2, c3, c4, wA, wB, p.sig, flags);
+                    cin = interp_coldens<true>(c1, c2, c3, c4, wA, wB, p.sig, flags);
                 }
                 const double cdho = finish_cell(cin, path, inv_np, flags, nHI_p, strength, pos, p, log2_tab);
                 __stcg(slab + pos, cdho);

@@ -116,9 +116,9 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, std::string& 
                 if (ia + ja + ka > Q) continue;
                 const int m = std::max(ia, std::max(ja, ka));
                 PlanCell pc;
-                pc.d[0] = (int8_t)i;
-                pc.d[1] = (int8_t)j;
-                pc.d[2] = (int8_t)k;
+                pc.d[0] = (uint8_t)(i - lo);
+                pc.d[1] = (uint8_t)(j - lo);
+                pc.d[2] = (uint8_t)(k - lo);
                 pc.pad = 0;
                 pc.flags = 0;
                 pc.nb[0] = pc.nb[1] = pc.nb[2] = pc.nb[3] = 0;
@@ -193,6 +193,8 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, std::string& 
     plan.q_max = Q;
     plan.nlevels = nlevels;
     plan.max_level_cells = maxc;
+    plan.lo = lo;
+    plan.side = side;
     plan.ncells = total;
 
     cudaError_t e = cudaMalloc(&plan.d_cells, sizeof(PlanCell) * (size_t)total);
