@@ -182,11 +182,12 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
             if (per_src > budget) {
                 plan_ok = false;
             } else {
-                // Launch shape (measured on B200, scripts/perf_probe.py): one source per CTA; 256 threads
-                // while a level is at most a few passes wide, 1024 once levels reach thousands of cells.
-                S = 1;
+                // Launch shape (measured on B200, scripts/perf_probe2.py): 256 threads while a level is
+                // at most a few passes wide, 1024 once levels reach thousands of cells; two sources per
+                // CTA (plan decode and barriers amortised) when both fit next to >= 3 resident CTAs.
                 const int maxc = g.plan.max_level_cells;
                 block = maxc >= 2048 ? 1024 : 256;
+                S = (block == 256 && count >= 8 * g.sm_count && 3 * sweep_smem_bytes(g.plan, 2) <= budget) ? 2 : 1;
                 if (g.tune_S > 0 && (size_t)g.tune_S * per_src <= budget) S = g.tune_S;
                 if (g.tune_block > 0) block = g.tune_block;
             }

@@ -223,8 +223,10 @@ __device__ __forceinline__ void fetch_cell(Fetched<S>& f, const PlanCell* __rest
 
 // One CTA per S sources.  Per level: every thread updates its cells (plan entry + neutral density from
 // global memory, four upstream column densities from the previous level's shared-memory buffer), then a
-// CTA barrier hands the level over.  (An explicitly software-pipelined version that prefetched the next
-// cell across the barrier was measured 30 % slower on B200 -- register pressure -- and dropped.)
+// CTA barrier hands the level over.  Two latency-hiding variants were measured on B200 and dropped: an
+// explicitly software-pipelined loop that held the next cell's plan entry and neutral density in
+// registers across the barrier (30 % slower: register pressure), and prefetch.global.L1 of the next plan
+// entry (4 % slower).
 template <int S, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
 sweep_smem_kernel(const PlanCell* __restrict__ plan, const int* __restrict__ level_start,
