@@ -1,0 +1,160 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports what include/asora_b200.h declares, the Python
+boundary mirrors the reference's signatures and error behaviour, and the multi-rank host logic
+(source sharding + phi_ion reduction) works over gloo with world_size 2."""
+import ctypes
+import inspect
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "asora_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(asora_\w+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pyc2ray_b200.lib import _cabi
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(_cabi.L, s), f"{s} declared in include/asora_b200.h but not exported"
+    assert sorted(_cabi.SIGNATURES) == syms, "ctypes signature table and header disagree"
+    assert b"sm_100a" in _cabi.L.asora_version()
+
+
+def test_cells_per_source_host_arithmetic():
+    import oracle
+    from pyc2ray_b200.lib import _cabi
+    for N, R in ((256, 10), (256, 10.76), (256, 30), (250, 30), (128, 1e9), (15, 7.3), (64, 20.0)):
+        assert _cabi.L.asora_cells_per_source(N, R) == oracle.cells_per_source(N, R)
+
+
+def test_no_cpu_fallback_and_error_reporting():
+    """Without a device every compute entry point fails loudly with a RuntimeError (never a silent CPU path,
+    never an abort), and the CPU-only halves of the reference API say so."""
+    import torch
+    import pyc2ray_b200 as p
+    from pyc2ray_b200.lib import libasora, libc2ray
+    with pytest.raises(NotImplementedError):
+        libc2ray.raytracing.do_all_sources()
+    with pytest.raises(NotImplementedError):
+        p.evolve3D(1.0, 1.0, np.ones(1), np.ones((3, 1)), False, 0, 0, 0, *([np.ones((2, 2, 2))] * 3), None, None, 0, 0,
+                   1, 1e-4, 0, 0, 0, 0, 0, 0)
+    with pytest.raises(RuntimeError, match="not initialized"):
+        p.evolve3D(1.0, 1.0, np.ones(1), np.ones((3, 1)), True, 0, 0, 0, *([np.ones((2, 2, 2))] * 3), np.ones(3), np.ones(3),
+                   0, 0, 1, 1e-4, 0, 0, 0, 0, 0, 0)
+    with pytest.raises(RuntimeError, match="not initialized"):
+        p.photo_table_to_device(np.ones(4), np.ones(4))
+    with pytest.raises(RuntimeError, match="not initialized"):
+        p.device_close()
+    with pytest.raises(RuntimeError, match="not initialized"):
+        libasora.density_to_device(np.zeros(8), 2)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="libasora_b200"):
+            p.device_init(8, 1)
+        assert not p.cuda_is_init()
+        with pytest.raises(RuntimeError, match="libasora_b200"):
+            libc2ray.chemistry.global_pass(1.0, *([np.ones((2, 2, 2))] * 6), 1, 1, 1, 1, 1)
+
+
+def test_boundary_signatures_match_reference():
+    """Positional signatures of the drop-in boundary (src/asora/python_module.cu:21-148, pyc2ray/evolve.py:38-46,
+    249-258, pyc2ray/raytracing.py:34-43, pyc2ray/asora_core.py)."""
+    import pyc2ray_b200 as p
+    from pyc2ray_b200.lib import libasora
+    sig = lambda f: list(inspect.signature(f).parameters)
+    assert sig(libasora.do_all_sources) == ["R", "coldensh_out", "sig", "dr", "ndens", "xh_av", "phi_ion", "NumSrc", "m1",
+                                            "minlogtau", "dlogtau", "NumTau"]
+    assert sig(libasora.device_init) == ["N", "num_src_par"]
+    assert sig(libasora.density_to_device) == ["ndens", "N"]
+    assert sig(libasora.photo_table_to_device) == ["thin_table", "thick_table", "NumTau"]
+    assert sig(libasora.source_data_to_device) == ["pos", "flux", "NumSrc"]
+    assert sig(p.evolve3D) == ["dt", "dr", "src_flux", "src_pos", "use_gpu", "max_subbox", "subboxsize", "loss_fraction",
+                               "temp", "ndens", "xh", "photo_thin_table", "photo_thick_table", "minlogtau", "dlogtau",
+                               "R_max_LLS", "convergence_fraction", "sig", "bh00", "albpow", "colh0", "temph0", "abu_c",
+                               "logfile", "quiet"]
+    assert sig(p.evolve3D_MPI)[:12] == ["dt", "dr", "src_flux", "src_pos", "use_gpu", "max_subbox", "subboxsize",
+                                        "loss_fraction", "use_mpi", "comm", "rank", "nprocs"]
+    assert sig(p.do_raytracing)[:9] == ["dr", "src_flux", "src_pos", "use_gpu", "max_subbox", "subboxsize", "loss_fraction",
+                                        "ndens", "xh_av"]
+    assert sig(p.hydrogenODE) == ["dt", "ndens", "temp", "xh", "phi_ion", "bh00", "albpow", "colh0", "abu_c"]
+    assert sig(p.device_init) == ["N", "source_batch_size"]
+
+
+def test_argument_checks_of_the_shim():
+    from pyc2ray_b200.lib import libasora
+    with pytest.raises(TypeError, match="coldensh_out must be Array of type double"):  # python_module.cu:53-57
+        libasora.do_all_sources(1.0, np.zeros(1, dtype=np.float32), 1.0, 1.0, None, np.zeros(8), np.zeros(8), 1, 2, -20.0, 0.1, 10)
+    with pytest.raises(TypeError):
+        libasora.source_data_to_device(np.zeros(3, dtype=np.int64), np.ones(1), 1)
+    with pytest.raises(ValueError):
+        libasora.density_to_device(np.zeros(7), 2)
+
+
+def test_shard_bounds_follow_reference_split():
+    """evolve.py:362-367: contiguous blocks of NumSrc//nprocs, remainder to the last rank."""
+    from pyc2ray_b200.parallel import shard_bounds
+    for ns, nprocs in ((10, 2), (10, 3), (7, 8), (100000, 8), (8, 8), (9, 4)):
+        covered = []
+        for r in range(nprocs):
+            a, b = shard_bounds(ns, r, nprocs)
+            assert b - a == ns // nprocs or r == nprocs - 1
+            covered += list(range(a, b))
+        assert covered == list(range(ns))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _rank_main(rank, world, port, outdir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import oracle
+    from pyc2ray_b200.parallel import shard_bounds, allreduce_sum_
+    from pyc2ray_b200.utils.sourceutils import format_sources
+    from tests.fields import make_case
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    c = make_case("multi_n32")
+    a, b = shard_bounds(c["flux"].size, rank, world)
+    pos_flat, flux_flat = format_sources(c["srcpos"][:, a:b], c["flux"][a:b])
+    phi, _, _ = oracle.asora_do_all_sources(c["R"], c["sig"], c["dr"], c["ndens"].ravel(), c["xh"].ravel(), pos_flat, flux_flat,
+                                            c["N"], c["thin"], c["thick"], c["minlogtau"], c["dlogtau"], c["NumTau"])
+    t = torch.from_numpy(phi)
+    allreduce_sum_(t)
+    np.save(os.path.join(outdir, f"phi_{rank}.npy"), t.numpy())
+    dist.destroy_process_group()
+
+
+def test_two_rank_source_sharding_over_gloo(tmp_path):
+    """world_size-2 run of the N>1 host logic on CPU: each rank ray-traces its shard (the oracle stands in for
+    the GPU sweep), the rate grids are summed with the same all-reduce helper the NCCL path uses, and every
+    rank ends with the single-process result."""
+    import torch.multiprocessing as mp
+    import oracle
+    from tests.fields import make_case
+    port = _free_port()
+    mp.spawn(_rank_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    c = make_case("multi_n32")
+    ref, _, _ = oracle.asora_do_all_sources(c["R"], c["sig"], c["dr"], c["ndens"].ravel(), c["xh"].ravel(), c["pos_flat"],
+                                            c["flux_flat"], c["N"], c["thin"], c["thick"], c["minlogtau"], c["dlogtau"],
+                                            c["NumTau"])
+    p0 = np.load(tmp_path / "phi_0.npy")
+    p1 = np.load(tmp_path / "phi_1.npy")
+    np.testing.assert_array_equal(p0, p1)
+    np.testing.assert_allclose(p0, ref, rtol=1e-13, atol=0)
