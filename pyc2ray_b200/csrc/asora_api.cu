@@ -30,6 +30,10 @@ struct Context {
     double2* thin = nullptr;   // {T[i], T[i+1]-T[i]} pairs (sweep_kernels.cu: photo_lookup)
     double2* thick = nullptr;
     int ntab = 0;
+    double* grid_scratch = nullptr;  // ngroups x N^3 column densities of the grid-cooperative sweep
+    int grid_scratch_groups = 0;
+    int grid_max_groups = 0;
+    unsigned* grid_counters = nullptr;
     double* nhi = nullptr;      // ndens * (1 - xh_av), rebuilt before every sweep
     double2* log2_tab = nullptr;
     int* src_pos = nullptr;      // as uploaded (positions reduced modulo N)
@@ -196,17 +200,39 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     }
     if (variant == 0) variant = plan_ok ? 1 : 2;
 
+    // host-side preparation of the grid-cooperative sweep (kept outside the timed region)
+    int groups = 1;
+    if (variant == 2) {
+        if (!p.coldens_out) {
+            // concurrent sources: one scratch grid per group, bounded by 1/4 of the free device memory
+            const size_t per = sizeof(double) * (size_t)g.ncell;
+            if (g.grid_max_groups == 0) {
+                size_t free_b = 0, total_b = 0;
+                CK(cudaMemGetInfo(&free_b, &total_b));
+                g.grid_max_groups = (int)std::min<size_t>(16, std::max<size_t>(1, (free_b / 4) / per));
+            }
+            groups = sweep_grid_groups(p, g.grid_max_groups, nullptr, nullptr);
+            if (groups < 1) return fail("sweep_grid_kernel: no resident CTAs");
+            if (groups > g.grid_scratch_groups) {
+                if (g.grid_scratch) cudaFree(g.grid_scratch);
+                g.grid_scratch = nullptr;
+                g.grid_scratch_groups = 0;
+    g.grid_max_groups = 0;
+                CK(cudaMalloc(&g.grid_scratch, per * groups));
+                g.grid_scratch_groups = groups;
+            }
+            p.coldens_out = g.grid_scratch;
+        }
+        if (!g.grid_counters) CK(cudaMalloc(&g.grid_counters, sizeof(unsigned) * 16));
+    }
+
     CK(cudaEventRecord(g.ev0, g.stream));
     if (variant == 1) {
         g.last_levels = g.plan.nlevels;
         cudaError_t e = launch_sweep_smem(g.plan, p, S, block, g.tune_regs, g.stream, &g.last_launches);
         if (e != cudaSuccess) return fail_cuda("sweep_smem_kernel launch", e);
     } else {
-        if (!p.coldens_out) {
-            if (int rc = ensure_buffer(ASORA_BUF_COLDENS)) return rc;
-            p.coldens_out = g.buf[ASORA_BUF_COLDENS];
-        }
-        cudaError_t e = launch_sweep_grid(p, g.stream, &g.last_launches, &g.last_levels);
+        cudaError_t e = launch_sweep_grid(p, groups, g.grid_counters, g.stream, &g.last_launches, &g.last_levels);
         if (e != cudaSuccess) return fail_cuda("sweep_grid_kernel launch", e);
     }
     CK(cudaEventRecord(g.ev1, g.stream));
@@ -268,6 +294,11 @@ int asora_device_close(void)
     if (g.thin) cudaFree(g.thin);
     if (g.thick) cudaFree(g.thick);
     if (g.nhi) cudaFree(g.nhi);
+    if (g.grid_scratch) cudaFree(g.grid_scratch);
+    if (g.grid_counters) cudaFree(g.grid_counters);
+    g.grid_scratch = nullptr;
+    g.grid_counters = nullptr;
+    g.grid_scratch_groups = 0;
     if (g.log2_tab) cudaFree(g.log2_tab);
     g.nhi = nullptr;
     g.log2_tab = nullptr;

@@ -93,7 +93,9 @@ void free_sweep_plan(SweepPlan& plan);
 size_t sweep_smem_bytes(const SweepPlan& plan, int sources_per_cta);
 cudaError_t launch_sweep_smem(const SweepPlan& plan, const SweepParams& p, int sources_per_cta, int block,
                               int regs_mode, cudaStream_t stream, int* launches);
-cudaError_t launch_sweep_grid(const SweepParams& p, cudaStream_t stream, int* launches, int* levels);
+int sweep_grid_groups(const SweepParams& p, int max_groups, int* total_ctas_out, int* group_ctas_out);
+cudaError_t launch_sweep_grid(const SweepParams& p, int ngroups, unsigned* counters, cudaStream_t stream,
+                              int* launches, int* levels);
 
 cudaError_t launch_prepare_nhi(const double* ndens, const double* xh_av, double* nhi, int64_t ncell, cudaStream_t stream);
 cudaError_t launch_pair_table(const double* table, double2* pairs, int ntab, cudaStream_t stream);

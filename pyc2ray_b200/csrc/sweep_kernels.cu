@@ -363,18 +363,44 @@ __device__ __forceinline__ void shell_cell(long long t, int m, int& di, int& dj,
 
 __device__ __forceinline__ int isign1(int x) { return x >= 0 ? 1 : -1; }
 
-__global__ void sweep_grid_kernel(SweepParams p, int nlevels)
+// Barrier among the `nctas` co-resident CTAs of one group (the launch is cooperative, so all CTAs of the
+// grid are resident).  Same structure as cooperative_groups' grid.sync(): CTA barrier, one thread
+// publishes with a fence + atomic and spins on the group's monotonically increasing counter, fence,
+// CTA barrier.  `epoch` counts the barriers this CTA has passed.
+__device__ __forceinline__ void group_barrier(unsigned* counter, unsigned nctas, unsigned& epoch)
 {
-    cg::grid_group grid = cg::this_grid();
+    __syncthreads();
+    epoch++;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const unsigned target = epoch * nctas;
+        while (*(volatile unsigned*)counter < target) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// The grid is split into `ngroups` groups of `group_ctas` CTAs; group g sweeps sources g, g+ngroups, ...
+// through its own N^3 scratch grid, so that sources whose levels are much narrower than the GPU run
+// side by side.  ngroups == 1 is "the whole GPU per source".
+__global__ void __launch_bounds__(512, 2)
+sweep_grid_kernel(SweepParams p, int nlevels, int ngroups, int group_ctas, unsigned* counters)
+{
     __shared__ double2 log2_tab[256];
     for (int t = threadIdx.x; t < 256; t += blockDim.x) log2_tab[t] = __ldg(p.log2_tab + t);
     __syncthreads();
     const int N = p.N;
-    const long long nthreads = (long long)gridDim.x * blockDim.x;
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    double* __restrict__ slab = p.coldens_out;
+    const int group = blockIdx.x / group_ctas;
+    if (group >= ngroups) return;  // spare CTAs of an uneven split
+    const long long nthreads = (long long)group_ctas * blockDim.x;
+    const long long tid = (long long)(blockIdx.x - group * group_ctas) * blockDim.x + threadIdx.x;
+    double* __restrict__ slab = p.coldens_out + (size_t)group * N * N * N;
+    unsigned* counter = counters + group;
+    unsigned epoch = 0;
 
-    for (int sidx = 0; sidx < p.src_count; sidx++) {
+    for (int sidx = group; sidx < p.src_count; sidx += ngroups) {
         const int ns = p.src_begin + sidx;
         const int i0 = p.src_pos[3 * ns + 0], j0 = p.src_pos[3 * ns + 1], k0 = p.src_pos[3 * ns + 2];
         const double strength = p.src_flux[ns];
@@ -435,30 +461,53 @@ __global__ void sweep_grid_kernel(SweepParams p, int nlevels)
                 const double cdho = finish_cell(cin, path, inv_np, flags, nHI_p, strength, pos, p, log2_tab);
                 __stcg(slab + pos, cdho);
             }
-            grid.sync();
+            group_barrier(counter, (unsigned)group_ctas, epoch);
         }
     }
 }
 
-cudaError_t launch_sweep_grid(const SweepParams& p, cudaStream_t stream, int* launches, int* levels)
+// Number of concurrent sources (groups) for the grid-cooperative sweep, at most `max_groups` (scratch grids).
+int sweep_grid_groups(const SweepParams& p, int max_groups, int* total_ctas_out, int* group_ctas_out)
+{
+    const int block = 512;
+    static int total_cached = 0;  // resident CTAs of the cooperative launch (device property, queried once)
+    if (total_cached == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_grid_kernel, block, 0) != cudaSuccess) return 0;
+        if (per_sm < 1) return 0;
+        total_cached = sms * per_sm;
+    }
+    const int total = total_cached;
+    // A level costs one pass of latency (~3 us) per ceil(cells / threads) plus one barrier (~2 us); more
+    // groups amortise the barrier over more sources (measured: scripts/perf_probe3.py), so take as many as
+    // there are scratch grids and sources, keeping at least 8 CTAs per group.
+    int groups = max(1, min(max_groups, p.src_count));
+    while (groups > 1 && total / groups < 8) groups--;
+    if (total_ctas_out) *total_ctas_out = total;
+    if (group_ctas_out) *group_ctas_out = total / groups;
+    return groups;
+}
+
+cudaError_t launch_sweep_grid(const SweepParams& p, int ngroups, unsigned* counters, cudaStream_t stream,
+                              int* launches, int* levels)
 {
     if (p.src_count <= 0) return cudaSuccess;
-    int dev = 0, sms = 0, per_sm = 0;
     const int block = 512;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_grid_kernel, block, 0);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    int total = 0, group_ctas = 0;
+    int check = sweep_grid_groups(p, ngroups, &total, &group_ctas);
+    if (check < 1) return cudaErrorLaunchOutOfResources;
+    group_ctas = total / ngroups;
     // levels 0..min(q_max, max(|last_l|, last_r))
     int nlevels = min(p.q_max, max(-p.last_l, p.last_r)) + 1;
     if (levels) *levels = nlevels;
+    cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(unsigned) * ngroups, stream);
+    if (e != cudaSuccess) return e;
     SweepParams pc = p;
-    void* args[] = {(void*)&pc, (void*)&nlevels};
+    void* args[] = {(void*)&pc, (void*)&nlevels, (void*)&ngroups, (void*)&group_ctas, (void*)&counters};
     if (launches) *launches += 1;
-    return cudaLaunchCooperativeKernel((void*)sweep_grid_kernel, dim3(sms * per_sm), dim3(block), args, 0, stream);
+    return cudaLaunchCooperativeKernel((void*)sweep_grid_kernel, dim3(total), dim3(block), args, 0, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------
