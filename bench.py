@@ -126,6 +126,40 @@ def cpu_reference_rate(R, nsrc_sample, threads, N=N_MESH, seed=100):
     return units / dt, dt, threads
 
 
+def eor_step(p, thin, thick, dlogtau, N=250, nsrc=100000):
+    """One full evolve3D time step of the c2ray_244paper configuration restated synthetically (the real
+    density / halo files are not in the reference checkout): 250^3, 10^5 seeded sources, R_max = 15 cMpc =
+    10.76 cells (test/paper_eor_simulation/parameters.yml:84), log-normal density, dt = 10 Myr.  Wall clock of
+    the whole call: uploads, every ray-tracing + chemistry iteration until convergence, downloads."""
+    from pyc2ray_b200.utils.sourceutils import generate_test_sources
+    rng = np.random.default_rng(244)
+    srcpos = generate_test_sources(N, nsrc, seed=244)
+    flux = 10 ** rng.normal(5.0, 0.5, size=nsrc)  # ~1e53 photons/s: a few cells ionised per source and step
+    g = rng.normal(size=(N, N, N))
+    ndens = 1.87e-7 * (1.0 + 9.0) ** 3 * np.exp(0.5 * g - 0.125)
+    xh = np.full((N, N, N), 2e-4)
+    temp = np.full((N, N, N), 1e4)
+    dr = 244.0 / 0.7 * MPC / N / (1.0 + 9.0)
+    R = 15.0 * N * 0.7 / 244.0
+    chem = (2.59e-13, -0.7, 1.3e-8 * 0.83 / 13.598 ** 2, 13.598 / 8.617e-5, 7.1e-7)
+    p.device_init(N, 96)
+    try:
+        p.photo_table_to_device(thin, thick)
+        best, niter, mean_x = None, 0, 0.0
+        for rep in range(2):
+            t0 = time.perf_counter()
+            x, phi = p.evolve3D(1e7 * 3.15576e7, dr, flux, srcpos, True, 1000, 64, 1e-2, temp, ndens, xh, thin, thick,
+                                -20.0, dlogtau, R, 1e-4, SIG, *chem, logfile=None, quiet=True)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+            niter, mean_x = p.evolve3D.last_niter, float(x.mean())
+    finally:
+        p.device_close()
+    return {"ms": 1e3 * best, "iterations": niter, "mean_xh_after": mean_x,
+            "config": f"synthetic c2ray_244paper step: {N}^3, {nsrc} sources, R={R:.2f} cells, dt=10 Myr, "
+                      "evolve3D incl. host<->device copies"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -166,6 +200,7 @@ def main():
     ap.add_argument("--nsrc", type=int, default=10000)
     ap.add_argument("--cpu-sample", type=int, default=512, help="sources per CPU-baseline step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-eor", action="store_true", help="skip the secondary EoR-step timing")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -277,6 +312,11 @@ def main():
 
     p.device_close()
 
+    # ---- secondary: one full EoR time step (BASELINE metric "EoR step time"), rank 0, single GPU ----------
+    eor = None
+    if rank == 0 and world == 1 and not args.no_eor:
+        eor = eor_step(p, thin, thick, dlogtau)
+
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -311,6 +351,8 @@ def main():
             "clocks": clocks,
             "phi_checksum": phi_checksum,
         }
+        if eor is not None:
+            line["eor_step"] = eor
         if not args.no_cpu:
             import oracle
             threads = oracle.max_threads()

@@ -96,6 +96,9 @@ void* asora_device_buffer(int which);
 int asora_buffer_upload(int which, const double* host);
 int asora_buffer_download(int which, double* host);
 
+/* Device -> device copy between two named buffers (N^3 doubles), on the context's stream. */
+int asora_buffer_copy(int dst, int src);
+
 /* Ray-trace sources [src_begin, src_begin+src_count) of the uploaded list using the device-resident
  * NDENS and XH_AV buffers; rates are accumulated into PHI_ION, which is zeroed first when
  * zero_phi != 0.  Asynchronous on the context's stream; asora_sync() waits. */

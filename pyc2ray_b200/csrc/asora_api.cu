@@ -493,6 +493,16 @@ int asora_buffer_download(int which, double* host)
     return 0;
 }
 
+int asora_buffer_copy(int dst, int src)
+{
+    if (int rc = need_init()) return rc;
+    if (int rc = ensure_buffer(dst)) return rc;
+    if (int rc = ensure_buffer(src)) return rc;
+    if (dst != src)
+        CK(cudaMemcpyAsync(g.buf[dst], g.buf[src], sizeof(double) * g.ncell, cudaMemcpyDeviceToDevice, g.stream));
+    return 0;
+}
+
 int asora_global_pass_device(double dt, double bh00, double albpow, double colh0, double temph0, double abu_c,
                              int* conv_flag, double* sum_xh1, double* sum_xh0)
 {

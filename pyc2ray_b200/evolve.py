@@ -22,8 +22,9 @@ __all__ = ["evolve3D", "evolve3D_MPI", "evolve3D_dist"]
 
 
 def _flat(a):
-    """float64 flat copy in logical C order (index i*N*N + j*N + k), as evolve.py:142-143."""
-    return np.ravel(a).astype("float64", copy=True)
+    """float64, flat, logical C order (index i*N*N + j*N + k), as evolve.py:142-143; a view when the input
+    already has that layout (the library only reads it)."""
+    return np.ascontiguousarray(np.ravel(a), dtype=np.float64)
 
 
 def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table, minlogtau, dlogtau, R_max_LLS,
@@ -49,11 +50,11 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
     NumSrc = normflux_flat.shape[0]
 
     check(L.asora_source_data_to_device(iptr(srcpos_flat), dptr(normflux_flat), NumSrc))
-    xh_flat = _flat(xh)
     check(L.asora_buffer_upload(_cabi.BUF_NDENS, dptr(_flat(ndens))))
     check(L.asora_buffer_upload(_cabi.BUF_TEMP, dptr(_flat(temp))))
-    for b in (_cabi.BUF_XH, _cabi.BUF_XH_AV, _cabi.BUF_XH_INTERMED):  # evolve.py:136-137
-        check(L.asora_buffer_upload(b, dptr(xh_flat)))
+    check(L.asora_buffer_upload(_cabi.BUF_XH, dptr(_flat(xh))))
+    for b in (_cabi.BUF_XH_AV, _cabi.BUF_XH_INTERMED):  # xh_av = xh_intermed = copy(xh): evolve.py:136-137
+        check(L.asora_buffer_copy(b, _cabi.BUF_XH))
     phi_t = None
     if nprocs > 1:
         phi_t = device_tensor(L.asora_device_buffer(_cabi.BUF_PHI_ION), NumCells)

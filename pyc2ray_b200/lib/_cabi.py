@@ -30,6 +30,7 @@ SIGNATURES = {
     "asora_device_buffer": (ctypes.c_void_p, [_i]),
     "asora_buffer_upload": (_i, [_i, c_dp]),
     "asora_buffer_download": (_i, [_i, c_dp]),
+    "asora_buffer_copy": (_i, [_i, _i]),
     "asora_raytrace_device": (_i, [_d, _d, _d, _i, _i, _d, _d, _i, _i]),
     "asora_global_pass_device": (_i, [_d, _d, _d, _d, _d, _d, ctypes.POINTER(_i), c_dp, c_dp]),
     "asora_sync": (_i, []),
