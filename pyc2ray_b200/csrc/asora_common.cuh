@@ -53,7 +53,10 @@ struct SweepPlan {
     int64_t ncells = 0;                // cells per source
     std::vector<int> level_start;      // nlevels+1
     std::vector<PlanCell> cells;       // level-major, lexicographic (di,dj,dk) inside a level
-    PlanCell* d_cells = nullptr;
+    // device copy, split into three 16-byte streams (structure of arrays): a warp's LDG.128 then covers 4
+    // contiguous 128-byte lines instead of 12 lines of a 48-byte-strided array of structures -- the L1/LSU
+    // wavefront pipe was the busiest unit of the sweep (82 % in profiles/r01c_sweep_smem_R30.txt)
+    int4* d_cells = nullptr;           // [3][ncells]: {wA,wB} | {path,inv_np} | {nb[4],d[3],flags,pad}
     int* d_level_start = nullptr;
     bool valid = false;
 };

@@ -196,13 +196,13 @@ struct Fetched {
 // cell coordinate already multiplied by its stride (N*N, N, 1): one LDS per axis replaces the
 // add / sign-fix / compare / select chain of modulo_gpu (raytracing.cu:24,270-272).
 template <int S>
-__device__ __forceinline__ void fetch_cell(Fetched<S>& f, const PlanCell* __restrict__ plan, int e,
+__device__ __forceinline__ void fetch_cell(Fetched<S>& f, const int4* __restrict__ plan, int ncells, int e,
                                            const unsigned* __restrict__ wrap_tab, int side,
                                            const double* __restrict__ nhi)
 {
-    // plan cell: three 16-byte read-only loads, shared by the S sources
-    const int4* q = reinterpret_cast<const int4*>(plan + e);
-    const int4 r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2);
+    // plan cell: three coalesced 16-byte read-only loads (one per stream), shared by the S sources
+    const int4 r2 = __ldg(plan + 2 * (size_t)ncells + e);
+    const int4 r0 = __ldg(plan + e), r1 = __ldg(plan + (size_t)ncells + e);
     f.wA = __hiloint2double(r0.y, r0.x);
     f.wB = __hiloint2double(r0.w, r0.z);
     f.path = __hiloint2double(r1.y, r1.x);
@@ -229,7 +229,7 @@ __device__ __forceinline__ void fetch_cell(Fetched<S>& f, const PlanCell* __rest
 // entry (4 % slower).
 template <int S, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
-sweep_smem_kernel(const PlanCell* __restrict__ plan, const int* __restrict__ level_start,
+sweep_smem_kernel(const int4* __restrict__ plan, int ncells, const int* __restrict__ level_start,
                                   int nlevels, int max_level_cells, int lo, int side, SweepParams p)
 {
     extern __shared__ double2 sh_raw[];
@@ -271,7 +271,7 @@ sweep_smem_kernel(const PlanCell* __restrict__ plan, const int* __restrict__ lev
         const double* prev = sh_cd + (size_t)((m & 1) ^ 1) * S * max_level_cells;
         for (int e = beg + threadIdx.x; e < end; e += BLOCK) {
             Fetched<S> c;
-            fetch_cell<S>(c, plan, e, wrap_tab, side, p.nhi);
+            fetch_cell<S>(c, plan, ncells, e, wrap_tab, side, p.nhi);
             const int slot = e - beg;
 #pragma unroll
             for (int s = 0; s < S; s++) {
@@ -300,8 +300,9 @@ static cudaError_t launch_smem_t(const SweepPlan& plan, const SweepParams& p, cu
     cudaError_t e = cudaFuncSetAttribute(sweep_smem_kernel<S, BLOCK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = (p.src_count + S - 1) / S;
-    sweep_smem_kernel<S, BLOCK, MINB><<<grid, BLOCK, smem, stream>>>(plan.d_cells, plan.d_level_start, plan.nlevels,
-                                                                   plan.max_level_cells, plan.lo, plan.side, p);
+    sweep_smem_kernel<S, BLOCK, MINB><<<grid, BLOCK, smem, stream>>>(plan.d_cells, (int)plan.ncells, plan.d_level_start,
+                                                                   plan.nlevels, plan.max_level_cells, plan.lo,
+                                                                   plan.side, p);
     return cudaGetLastError();
 }
 

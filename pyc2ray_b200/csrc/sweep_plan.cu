@@ -197,10 +197,17 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, std::string& 
     plan.side = side;
     plan.ncells = total;
 
-    cudaError_t e = cudaMalloc(&plan.d_cells, sizeof(PlanCell) * (size_t)total);
+    std::vector<int4> soa(3 * (size_t)total);
+    for (int64_t e = 0; e < total; e++) {
+        const int4* src = reinterpret_cast<const int4*>(&plan.cells[e]);
+        soa[e] = src[0];
+        soa[total + e] = src[1];
+        soa[2 * total + e] = src[2];
+    }
+    cudaError_t e = cudaMalloc(&plan.d_cells, sizeof(int4) * soa.size());
     if (e == cudaSuccess) e = cudaMalloc(&plan.d_level_start, sizeof(int) * (nlevels + 1));
     if (e == cudaSuccess)
-        e = cudaMemcpy(plan.d_cells, plan.cells.data(), sizeof(PlanCell) * (size_t)total, cudaMemcpyHostToDevice);
+        e = cudaMemcpy(plan.d_cells, soa.data(), sizeof(int4) * soa.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess)
         e = cudaMemcpy(plan.d_level_start, plan.level_start.data(), sizeof(int) * (nlevels + 1),
                        cudaMemcpyHostToDevice);
