@@ -52,6 +52,11 @@ struct Context {
     // stats of the last sweep
     int variant_forced = 0;
     int tune_S = 0, tune_block = 0, tune_regs = 0, tune_zface = 0;
+    int sphere_only = 0;
+    // cached rated-cell count (sphere-only statistics)
+    int rated_N = 0;
+    double rated_R = 0, rated_dr = 0;
+    int64_t rated_cells = 0;
     int last_variant = 0, last_launches = 0, last_qmax = 0, last_levels = 0;
     int64_t last_updates = 0;
     float last_ms = 0.f;
@@ -153,11 +158,23 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     p.src_flux = whole ? g.src_flux_sorted : g.src_flux;
     p.src_begin = begin;
     p.src_count = count;
+    const bool sphere_only = g.sphere_only && !coldens_grid;  // the debug path keeps the reference's cell set
+    p.sphere_only = sphere_only ? 1 : 0;
     p.coldens_out = coldens_grid;
 
     g.last_qmax = p.q_max;
     g.last_launches = 0;
-    g.last_updates = (int64_t)count * asora_count_cells(N, R);
+    if (sphere_only) {
+        if (!(g.rated_N == N && g.rated_R == R && g.rated_dr == dr)) {
+            g.rated_cells = asora_count_rated_cells(N, R, dr);
+            g.rated_N = N;
+            g.rated_R = R;
+            g.rated_dr = dr;
+        }
+        g.last_updates = (int64_t)count * g.rated_cells;
+    } else {
+        g.last_updates = (int64_t)count * asora_count_cells(N, R);
+    }
     g.last_ms = 0.f;
 
     // Variant selection: the shared-memory sweep needs two levels of column densities per source.
@@ -167,9 +184,9 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     if (variant != 2) {
         const int lo_side = 2 * std::min(p.q_max, std::max(-p.last_l, p.last_r)) + 1;
         if (p.q_max <= 127 && lo_side <= 255) {
-            if (!(g.plan.valid && g.plan.N == N && g.plan.R == R && g.plan.dr == dr)) {
+            if (!(g.plan.valid && g.plan.N == N && g.plan.R == R && g.plan.dr == dr && g.plan.sphere_only == sphere_only)) {
                 std::string err;
-                if (!build_sweep_plan(g.plan, N, R, dr, err)) {
+                if (!build_sweep_plan(g.plan, N, R, dr, sphere_only, err)) {
                     if (variant == 1) return fail(err);
                 }
             }
@@ -585,6 +602,12 @@ int asora_set_sweep_variant(int variant)
 {
     if (variant < 0 || variant > 2) return fail("set_sweep_variant: unknown variant");
     g.variant_forced = variant;
+    return 0;
+}
+
+int asora_set_sphere_only(int sphere_only)
+{
+    g.sphere_only = sphere_only ? 1 : 0;
     return 0;
 }
 

@@ -53,6 +53,7 @@ struct SweepPlan {
     int nlevels = 0;
     int max_level_cells = 0;
     int lo = 0, side = 0;              // offsets span [lo, lo+side) on every axis
+    bool sphere_only = false;          // unrated cells left out (asora_set_sphere_only)
     int64_t ncells = 0;                // cells per source
     std::vector<int> level_start;      // nlevels+1
     std::vector<PlanCell> cells;       // level-major, lexicographic (di,dj,dk) inside a level
@@ -87,6 +88,7 @@ struct SweepParams {
     const int* src_pos;
     const double* src_flux;
     int src_begin, src_count;
+    int sphere_only;          // grid-cooperative variant: skip cells outside the R sphere
     double* coldens_out;      // optional N^3 grid receiving outgoing column densities (debug) or
                               // the L2-resident scratch of the grid-cooperative variant
 };
@@ -94,7 +96,8 @@ struct SweepParams {
 // host-side helpers implemented in sweep_plan.cu
 int asora_qmax(int N, double R);
 int64_t asora_count_cells(int N, double R);
-bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, std::string& err);
+bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_only, std::string& err);
+int64_t asora_count_rated_cells(int N, double R, double dr);
 void free_sweep_plan(SweepPlan& plan);
 
 // launchers implemented in sweep_kernels.cu

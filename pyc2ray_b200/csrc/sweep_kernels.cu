@@ -437,10 +437,17 @@ sweep_grid_kernel(SweepParams p, int nlevels, int ngroups, int group_ctas, unsig
                 if (di < p.last_l || di > p.last_r || dj < p.last_l || dj > p.last_r || dk < p.last_l ||
                     dk > p.last_r)
                     continue;
+                unsigned flags = 0;
+                if (m > 0) {
+                    // sphere test in the reference's own form (raytracing.cu:302-305,315)
+                    const double xs = p.dr * (double)di, ys = p.dr * (double)dj, zs = p.dr * (double)dk;
+                    const double dist2 = __fma_rn(zs, zs, __fma_rn(ys, ys, __dmul_rn(xs, xs)));
+                    if (dist2 / (p.dr * p.dr) <= p.R2) flags |= PC_RATED;
+                    else if (p.sphere_only) continue;
+                }
                 const int i = wrap(i0 + di, N), j = wrap(j0 + dj, N), k = wrap(k0 + dk, N);
                 const size_t pos = ((size_t)i * N + j) * N + k;
                 const double nHI_p = __ldg(p.nhi + pos);
-                unsigned flags = 0;
                 double cin = 0.0, path = 0.5, inv_np = ASORA_FOURPI;
                 if (m == 0) {
                     flags = PC_SOURCE | PC_RATED;
@@ -469,10 +476,6 @@ sweep_grid_kernel(SweepParams p, int nlevels, int ngroups, int group_ctas, unsig
                     path = sqrt((da * da + db * db) / (dc * dc) + 1.0);
                     inv_np = 1.0 / ((double)(ia * ia + ja * ja + ka * ka) * path);
                     if (c == 1 && (a == 1 || b == 1)) flags |= (a == 1 && b == 1) ? PC_DIAG3 : PC_DIAG2;
-                    // sphere test in the reference's own form (raytracing.cu:302-305,315)
-                    const double xs = p.dr * (double)di, ys = p.dr * (double)dj, zs = p.dr * (double)dk;
-                    const double dist2 = __fma_rn(zs, zs, __fma_rn(ys, ys, __dmul_rn(xs, xs)));
-                    if (dist2 / (p.dr * p.dr) <= p.R2) flags |= PC_RATED;
                     // the scratch grid is written by other SMs: read it at L2 (ld.global.cg), and skip
                     // zero-weight corners, which may never have been written for this source
                     const double c1 = (wA * wB != 0.0) ? __ldcg(slab + q1) : 0.0;
@@ -524,6 +527,8 @@ cudaError_t launch_sweep_grid(const SweepParams& p, int ngroups, unsigned* count
     group_ctas = total / ngroups;
     // levels 0..min(q_max, max(|last_l|, last_r))
     int nlevels = min(p.q_max, max(-p.last_l, p.last_r)) + 1;
+    // sphere-only: no cell beyond Chebyshev distance floor(R) can be inside the sphere
+    if (p.sphere_only && sqrt(p.R2) + 2.0 < (double)nlevels) nlevels = (int)sqrt(p.R2) + 2;
     if (levels) *levels = nlevels;
     cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(unsigned) * ngroups, stream);
     if (e != cudaSuccess) return e;

@@ -46,7 +46,32 @@ int64_t asora_count_cells(int N, double R)
 
 static inline int sign1(int x) { return x >= 0 ? 1 : -1; }  // raytracing.cu:27
 
-bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, std::string& err)
+// Sphere test exactly as the reference kernel evaluates it (raytracing.cu:302-305,315), nvcc contracting
+// xs*xs+ys*ys+zs*zs into DMUL,DFMA,DFMA (confirmed against the reference kernel on B200:
+// tests/test_gpu_vs_reference_kernel.py, case r_int5).
+static inline bool cell_rated(int i, int j, int k, double dr, double R2)
+{
+    const double xs = dr * (double)i, ys = dr * (double)j, zs = dr * (double)k;
+    const double dist2 = std::fma(zs, zs, std::fma(ys, ys, xs * xs));
+    return dist2 / (dr * dr) <= R2;
+}
+
+// cells of octahedron(q_max) & cube that receive a rate
+int64_t asora_count_rated_cells(int N, double R, double dr)
+{
+    const int Q = asora_qmax(N, R);
+    int ll, lr;
+    clip_bounds(N, ll, lr);
+    const int lo = std::max(ll, -Q), hi = std::min(lr, Q);
+    int64_t cnt = 0;
+    for (int i = lo; i <= hi; i++)
+        for (int j = lo; j <= hi; j++)
+            for (int k = lo; k <= hi; k++)
+                if (std::abs(i) + std::abs(j) + std::abs(k) <= Q && cell_rated(i, j, k, dr, R * R)) cnt++;
+    return cnt;
+}
+
+bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_only, std::string& err)
 {
     free_sweep_plan(plan);
     const int Q = asora_qmax(N, R);
@@ -58,15 +83,23 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, std::string& 
         err = "sweep plan: radius too large for the shared-memory variant";
         return false;
     }
-    const int nlevels = std::max(-lo, hi) + 1;
+    int nlevels = std::max(-lo, hi) + 1;
+    const double R2 = R * R;
+    auto rated = [&](int i, int j, int k) { return cell_rated(i, j, k, dr, R2); };
+    // membership: inside the octahedron, and inside the sphere when only rated cells are swept
+    auto member = [&](int i, int j, int k) {
+        if (std::abs(i) + std::abs(j) + std::abs(k) > Q) return false;
+        return !sphere_only || rated(i, j, k);
+    };
     // pass 1: level sizes
     std::vector<int> count(nlevels, 0);
     for (int i = lo; i <= hi; i++)
         for (int j = lo; j <= hi; j++)
             for (int k = lo; k <= hi; k++) {
-                if (std::abs(i) + std::abs(j) + std::abs(k) > Q) continue;
+                if (!member(i, j, k)) continue;
                 count[std::max(std::abs(i), std::max(std::abs(j), std::abs(k)))]++;
             }
+    while (nlevels > 1 && count[nlevels - 1] == 0) nlevels--;  // sphere-only: the outer levels may be empty
     plan.level_start.assign(nlevels + 1, 0);
     int maxc = 0;
     for (int m = 0; m < nlevels; m++) {
@@ -83,27 +116,18 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, std::string& 
     // pass 2: slots = rank inside the level, rated cells first, lexicographic inside each group
     std::vector<int32_t> slot((size_t)side * side * side, -1);
     auto sidx = [&](int i, int j, int k) { return ((size_t)(i - lo) * side + (j - lo)) * side + (k - lo); };
-    const double R2 = R * R;
-    // Sphere test exactly as the reference kernel evaluates it (raytracing.cu:302-305,315), nvcc
-    // contracting xs*xs+ys*ys+zs*zs into DMUL,DFMA,DFMA (confirmed against the reference kernel on
-    // B200: tests/test_gpu_vs_reference_kernel.py, case r_int5).
-    auto rated = [&](int i, int j, int k) {
-        const double xs = dr * (double)i, ys = dr * (double)j, zs = dr * (double)k;
-        const double dist2 = std::fma(zs, zs, std::fma(ys, ys, xs * xs));
-        return dist2 / (dr * dr) <= R2;
-    };
     {
         std::vector<int> fill_rated(nlevels, 0), nrated(nlevels, 0), fill_un(nlevels, 0);
         for (int i = lo; i <= hi; i++)
             for (int j = lo; j <= hi; j++)
                 for (int k = lo; k <= hi; k++) {
-                    if (std::abs(i) + std::abs(j) + std::abs(k) > Q) continue;
+                    if (!member(i, j, k)) continue;
                     if (rated(i, j, k)) nrated[std::max(std::abs(i), std::max(std::abs(j), std::abs(k)))]++;
                 }
         for (int i = lo; i <= hi; i++)
             for (int j = lo; j <= hi; j++)
                 for (int k = lo; k <= hi; k++) {
-                    if (std::abs(i) + std::abs(j) + std::abs(k) > Q) continue;
+                    if (!member(i, j, k)) continue;
                     int m = std::max(std::abs(i), std::max(std::abs(j), std::abs(k)));
                     slot[sidx(i, j, k)] = rated(i, j, k) ? fill_rated[m]++ : nrated[m] + fill_un[m]++;
                 }
@@ -113,7 +137,7 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, std::string& 
         for (int j = lo; j <= hi; j++)
             for (int k = lo; k <= hi; k++) {
                 const int ia = std::abs(i), ja = std::abs(j), ka = std::abs(k);
-                if (ia + ja + ka > Q) continue;
+                if (!member(i, j, k)) continue;
                 const int m = std::max(ia, std::max(ja, ka));
                 PlanCell pc;
                 pc.d[0] = (uint8_t)(i - lo);
@@ -196,6 +220,7 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, std::string& 
     plan.max_level_cells = maxc;
     plan.lo = lo;
     plan.side = side;
+    plan.sphere_only = sphere_only;
     plan.ncells = total;
 
     std::vector<int4> soa(3 * (size_t)total);

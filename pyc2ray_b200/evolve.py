@@ -67,41 +67,47 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
         printlog(f"Mean density (cgs): {ndens.mean():.3e}, Mean ionized fraction: {xh.mean():.3e}", logfile, quiet)
         printlog(f"Convergence Criterion (Number of points): {conv_criterion : n}", logfile, quiet, end="\n\n")
 
+    # The evolve loop only consumes phi_ion, so the sweep may skip the cells outside the R_max sphere
+    # (identical rates, see asora_set_sphere_only in include/asora_b200.h).
+    check(L.asora_set_sphere_only(1))
     converged = False
     niter = 0
     flag = ctypes.c_int(0)
     s1 = ctypes.c_double(0.0)
     s0 = ctypes.c_double(0.0)
-    while not converged:
-        niter += 1
-        trt0 = time.time()
-        check(L.asora_raytrace_device(float(R_max_LLS), float(sig), float(dr), 0, NumSrc, float(minlogtau),
-                                      float(dlogtau), int(NumTau), 1))
-        check(L.asora_sync())
-        if nprocs > 1:
-            import torch
-            allreduce_sum_(phi_t, group)  # evolve.py:433-437 (Reduce + Bcast) as one NCCL all-reduce
-            torch.cuda.synchronize()
-        trt = time.time() - trt0
-        tch0 = time.time()
-        check(L.asora_global_pass_device(float(dt), float(bh00), float(albpow), float(colh0), float(temph0),
-                                         float(abu_c), ctypes.byref(flag), ctypes.byref(s1), ctypes.byref(s0)))
-        tch = time.time() - tch0
-        conv_flag = flag.value
-        sum_xh1_int, sum_xh0_int = s1.value, s0.value
-        # evolve.py:216-232
-        rel_change_xh1 = abs((sum_xh1_int - prev_sum_xh1_int) / sum_xh1_int) if sum_xh1_int > 0.0 else 1.0
-        rel_change_xh0 = abs((sum_xh0_int - prev_sum_xh0_int) / sum_xh0_int) if sum_xh0_int > 0.0 else 1.0
-        if rank == 0:
-            printlog(f"Raytracing took {trt:.3f} s, chemistry {tch:.3f} s. Number of non-converged points: {conv_flag} "
-                     f"of {NumCells} ({conv_flag / NumCells * 100 : .3f} % ), Relative change in ionfrac: "
-                     f"{rel_change_xh1 : .2e}", logfile, quiet)
-        converged = (conv_flag < conv_criterion) or ((rel_change_xh1 < convergence_fraction) and
-                                                     (rel_change_xh0 < convergence_fraction))
-        prev_sum_xh1_int = sum_xh1_int
-        prev_sum_xh0_int = sum_xh0_int
-        if niter >= max_iter:
-            raise RuntimeError("evolve3D: no convergence")
+    try:
+        while not converged:
+            niter += 1
+            trt0 = time.time()
+            check(L.asora_raytrace_device(float(R_max_LLS), float(sig), float(dr), 0, NumSrc, float(minlogtau),
+                                          float(dlogtau), int(NumTau), 1))
+            check(L.asora_sync())
+            if nprocs > 1:
+                import torch
+                allreduce_sum_(phi_t, group)  # evolve.py:433-437 (Reduce + Bcast) as one NCCL all-reduce
+                torch.cuda.synchronize()
+            trt = time.time() - trt0
+            tch0 = time.time()
+            check(L.asora_global_pass_device(float(dt), float(bh00), float(albpow), float(colh0), float(temph0),
+                                             float(abu_c), ctypes.byref(flag), ctypes.byref(s1), ctypes.byref(s0)))
+            tch = time.time() - tch0
+            conv_flag = flag.value
+            sum_xh1_int, sum_xh0_int = s1.value, s0.value
+            # evolve.py:216-232
+            rel_change_xh1 = abs((sum_xh1_int - prev_sum_xh1_int) / sum_xh1_int) if sum_xh1_int > 0.0 else 1.0
+            rel_change_xh0 = abs((sum_xh0_int - prev_sum_xh0_int) / sum_xh0_int) if sum_xh0_int > 0.0 else 1.0
+            if rank == 0:
+                printlog(f"Raytracing took {trt:.3f} s, chemistry {tch:.3f} s. Number of non-converged points: "
+                         f"{conv_flag} of {NumCells} ({conv_flag / NumCells * 100 : .3f} % ), Relative change in "
+                         f"ionfrac: {rel_change_xh1 : .2e}", logfile, quiet)
+            converged = (conv_flag < conv_criterion) or ((rel_change_xh1 < convergence_fraction) and
+                                                         (rel_change_xh0 < convergence_fraction))
+            prev_sum_xh1_int = sum_xh1_int
+            prev_sum_xh0_int = sum_xh0_int
+            if niter >= max_iter:
+                raise RuntimeError("evolve3D: no convergence")
+    finally:
+        L.asora_set_sphere_only(0)
     if rank == 0:
         printlog("Multiple source convergence reached.", logfile, quiet)
     xh_new = np.empty(NumCells)

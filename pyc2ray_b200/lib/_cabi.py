@@ -38,6 +38,7 @@ SIGNATURES = {
     "asora_debug_single_source": (_i, [_d, _d, _d, c_dp, _i, _d, _d, _i, c_dp, c_dp]),
     "asora_set_sweep_variant": (_i, [_i]),
     "asora_set_tuning": (_i, [_i, _i]),
+    "asora_set_sphere_only": (_i, [_i]),
     "asora_last_sweep_stats": (_i, [ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i64),
                                     ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_float)]),
     "asora_cells_per_source": (_i64, [_i, _d]),

@@ -253,3 +253,26 @@ def test_errors_are_reported_not_thrown(libs):
                                     np.zeros(512), 1, 8, -20.0, 0.012, 2001)
     finally:
         libasora.device_close()
+
+
+@pytest.mark.parametrize("name", ["small_r5", "r_int5", "multi_n32", "mid_n48_r14", "clip_full_n24"])
+@pytest.mark.parametrize("variant", [1, 2])
+def test_sphere_only_sweep_gives_identical_rates(libs, name, variant):
+    """asora_set_sphere_only: skipping the octahedron's cells outside the R sphere must not change phi_ion
+    (they are never upstream of a rated cell), while the number of updates drops to the rated cells."""
+    oracle, p, _cabi, libasora = libs
+    from tests.fields import make_case
+    c = make_case(name)
+    _setup(libasora, c)
+    try:
+        full, _, upd_full = _sweep(libasora, _cabi, c, variant)
+        _cabi.check(_cabi.L.asora_set_sphere_only(1))
+        sph, _, upd_sph = _sweep(libasora, _cabi, c, variant)
+    finally:
+        _cabi.L.asora_set_sphere_only(0)
+        libasora.device_close()
+    assert upd_sph == int(np.count_nonzero(full)) if c["flux_flat"].size == 1 else upd_sph <= upd_full
+    if c["flux_flat"].size == 1:
+        np.testing.assert_array_equal(sph, full)  # one add per cell: bit-identical
+    else:
+        _assert_close(sph, full, f"{name} sphere-only", rtol=1e-13, floor=1e-15)
