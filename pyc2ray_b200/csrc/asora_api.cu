@@ -52,6 +52,7 @@ struct Context {
     // stats of the last sweep
     int variant_forced = 0;
     int tune_S = 0, tune_block = 0, tune_regs = 0, tune_zface = 0;
+    int tune_parts = 0;
     int sphere_only = 0;
     // cached rated-cell count (sphere-only statistics)
     int rated_N = 0;
@@ -184,11 +185,23 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     if (variant != 2) {
         const int lo_side = 2 * std::min(p.q_max, std::max(-p.last_l, p.last_r)) + 1;
         if (p.q_max <= 127 && lo_side <= 255) {
-            if (!(g.plan.valid && g.plan.N == N && g.plan.R == R && g.plan.dr == dr && g.plan.sphere_only == sphere_only)) {
-                std::string err;
-                if (!build_sweep_plan(g.plan, N, R, dr, sphere_only, err)) {
-                    if (variant == 1) return fail(err);
+            // Parts: start from the whole sweep and split (half-spaces, quadrants, octants) only until one
+            // source's two level buffers fit in shared memory.  (Measured at R = 30, 256^3: 1 part x 1024
+            // threads 20.6 ms, 2 x 512: 21.4, 4 x 256: 21.2, 8 x 256 with two sources: 21.1 -- splitting does
+            // not pay by itself, it extends the shared-memory variant to radii of ~65 cells.)
+            int parts = g.tune_parts > 0 ? g.tune_parts : 1;
+            for (;;) {
+                if (!(g.plan.valid && g.plan.N == N && g.plan.R == R && g.plan.dr == dr &&
+                      g.plan.sphere_only == sphere_only && g.plan.parts == parts)) {
+                    std::string err;
+                    if (!build_sweep_plan(g.plan, N, R, dr, sphere_only, parts, err)) {
+                        if (variant == 1) return fail(err);
+                        break;
+                    }
                 }
+                if (g.tune_parts > 0 || parts == 8) break;
+                if (sweep_smem_bytes(g.plan, 1) <= (size_t)g.smem_optin) break;
+                parts *= 2;
             }
             plan_ok = g.plan.valid;
         }
@@ -198,11 +211,12 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
             if (per_src > budget) {
                 plan_ok = false;
             } else {
-                // Launch shape (measured on B200, scripts/perf_probe2.py): 256 threads while a level is
-                // at most a few passes wide, 1024 once levels reach thousands of cells; two sources per
-                // CTA (plan decode and barriers amortised) when both fit next to >= 3 resident CTAs.
+                // Launch shape (measured on B200, scripts/perf_probe4.py): 256 threads while a level is at
+                // most a few passes wide, 512 for wider levels when two CTAs fit per SM, 1024 when only one
+                // does; two sources per CTA (plan decode and barriers amortised) when both fit next to >= 3
+                // resident CTAs.
                 const int maxc = g.plan.max_level_cells;
-                block = maxc >= 2048 ? 1024 : 256;
+                block = maxc < 2048 ? 256 : (2 * per_src <= budget ? 512 : 1024);
                 S = (block == 256 && count >= 8 * g.sm_count && 3 * sweep_smem_bytes(g.plan, 2) <= budget) ? 2 : 1;
                 if (g.tune_S > 0 && (size_t)g.tune_S * per_src <= budget) S = g.tune_S;
                 if (g.tune_block > 0) block = g.tune_block;
@@ -616,6 +630,7 @@ int asora_set_tuning(int sources_per_cta, int block_threads)
     // bit 16 of block_threads selects the relaxed register mode (profiling knob)
     g.tune_regs = (block_threads >> 16) & 1;
     g.tune_zface = (block_threads >> 17) & 3;  // bits 17-18: 1 = force the transposed z-face path, 2 = forbid it
+    g.tune_parts = (block_threads >> 20) & 15; // bits 20-23: parts per source (1, 2, 4, 8), 0 = automatic
     block_threads &= 0xffff;
     if (!(sources_per_cta == 0 || sources_per_cta == 1 || sources_per_cta == 2 || sources_per_cta == 4))
         return fail("set_tuning: sources_per_cta must be 0, 1, 2 or 4");

@@ -54,8 +54,9 @@ struct SweepPlan {
     int max_level_cells = 0;
     int lo = 0, side = 0;              // offsets span [lo, lo+side) on every axis
     bool sphere_only = false;          // unrated cells left out (asora_set_sphere_only)
-    int64_t ncells = 0;                // cells per source
-    std::vector<int> level_start;      // nlevels+1
+    int parts = 1;                     // independent pieces per source (sweep_plan.cu), one CTA each
+    int64_t ncells = 0;                // plan entries (all parts; bounding planes appear once per part)
+    std::vector<int> level_start;      // [parts][nlevels+1], absolute entry offsets
     std::vector<PlanCell> cells;       // level-major, lexicographic (di,dj,dk) inside a level
     // device copy, split into three 16-byte streams (structure of arrays): a warp's LDG.128 then covers 4
     // contiguous 128-byte lines instead of 12 lines of a 48-byte-strided array of structures -- the L1/LSU
@@ -96,7 +97,7 @@ struct SweepParams {
 // host-side helpers implemented in sweep_plan.cu
 int asora_qmax(int N, double R);
 int64_t asora_count_cells(int N, double R);
-bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_only, std::string& err);
+bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_only, int parts, std::string& err);
 int64_t asora_count_rated_cells(int N, double R, double dr);
 void free_sweep_plan(SweepPlan& plan);
 

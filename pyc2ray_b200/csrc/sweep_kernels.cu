@@ -245,15 +245,18 @@ __device__ __forceinline__ void fetch_cell(Fetched<S>& f, const int4* __restrict
 // entry (4 % slower).
 template <int S, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
-sweep_smem_kernel(const int4* __restrict__ plan, int ncells, const int* __restrict__ level_start,
-                                  int nlevels, int max_level_cells, int lo, int side, SweepParams p)
+sweep_smem_kernel(const int4* __restrict__ plan, int ncells, const int* __restrict__ level_start_all,
+                                  int nlevels, int max_level_cells, int lo, int side, int parts, SweepParams p)
 {
     extern __shared__ double2 sh_raw[];
     double2* log2_tab = sh_raw;                                 // 256 entries
     double* sh_cd = reinterpret_cast<double*>(sh_raw + 256);    // [2][S][max_level_cells]
     unsigned* wrap_tab = reinterpret_cast<unsigned*>(sh_cd + (size_t)2 * S * max_level_cells);  // [2][S][3][side]
     const int N = p.N;
-    const int first = blockIdx.x * S;
+    // CTA -> (group of S sources, part of the sweep)
+    const int part = blockIdx.x % parts;
+    const int first = (blockIdx.x / parts) * S;
+    const int* __restrict__ level_start = level_start_all + part * (nlevels + 1);
 
     for (int t = threadIdx.x; t < 256; t += BLOCK) log2_tab[t] = __ldg(p.log2_tab + t);
     // the source cell "interpolates" slot 0 of the (empty) previous level with weight 1: seed it with 0
@@ -321,10 +324,10 @@ static cudaError_t launch_smem_t(const SweepPlan& plan, const SweepParams& p, cu
     const size_t smem = sweep_smem_bytes(plan, S);
     cudaError_t e = cudaFuncSetAttribute(sweep_smem_kernel<S, BLOCK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int grid = (p.src_count + S - 1) / S;
+    const int grid = ((p.src_count + S - 1) / S) * plan.parts;
     sweep_smem_kernel<S, BLOCK, MINB><<<grid, BLOCK, smem, stream>>>(plan.d_cells, (int)plan.ncells, plan.d_level_start,
                                                                    plan.nlevels, plan.max_level_cells, plan.lo,
-                                                                   plan.side, p);
+                                                                   plan.side, plan.parts, p);
     return cudaGetLastError();
 }
 

@@ -71,9 +71,20 @@ int64_t asora_count_rated_cells(int N, double R, double dr)
     return cnt;
 }
 
-bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_only, std::string& err)
+// One sweep may be split into `parts` in {1,2,4,8} independent pieces by the signs of the offsets on z,
+// (y,z) or (x,y,z): every non-zero interpolation weight points one step towards the source, so a cell's
+// upstream cells have offsets of the same sign or zero, and a zero offset only ever pairs with the weight of
+// the unstepped corner.  A part therefore consists of its open half-space / quadrant / octant plus the
+// bounding planes (offset 0 on a constrained axis); the planes are recomputed by every part that touches
+// them but receive their rate from the all-positive side only ("owned" cells keep PC_RATED).  Parts of one
+// source run as separate CTAs with 1/parts of the shared memory each.
+bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_only, int parts, std::string& err)
 {
     free_sweep_plan(plan);
+    if (!(parts == 1 || parts == 2 || parts == 4 || parts == 8)) {
+        err = "sweep plan: parts must be 1, 2, 4 or 8";
+        return false;
+    }
     const int Q = asora_qmax(N, R);
     int ll, lr;
     clip_bounds(N, ll, lr);
@@ -86,132 +97,153 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_o
     int nlevels = std::max(-lo, hi) + 1;
     const double R2 = R * R;
     auto rated = [&](int i, int j, int k) { return cell_rated(i, j, k, dr, R2); };
-    // membership: inside the octahedron, and inside the sphere when only rated cells are swept
+    auto level_of = [](int i, int j, int k) { return std::max(std::abs(i), std::max(std::abs(j), std::abs(k))); };
+    // membership of the sweep: inside the octahedron, and inside the sphere when only rated cells are swept
     auto member = [&](int i, int j, int k) {
         if (std::abs(i) + std::abs(j) + std::abs(k) > Q) return false;
         return !sphere_only || rated(i, j, k);
     };
-    // pass 1: level sizes
-    std::vector<int> count(nlevels, 0);
-    for (int i = lo; i <= hi; i++)
-        for (int j = lo; j <= hi; j++)
-            for (int k = lo; k <= hi; k++) {
-                if (!member(i, j, k)) continue;
-                count[std::max(std::abs(i), std::max(std::abs(j), std::abs(k)))]++;
-            }
-    while (nlevels > 1 && count[nlevels - 1] == 0) nlevels--;  // sphere-only: the outer levels may be empty
-    plan.level_start.assign(nlevels + 1, 0);
+    {   // trailing levels may be empty in sphere-only mode
+        std::vector<char> used(nlevels, 0);
+        for (int i = lo; i <= hi; i++)
+            for (int j = lo; j <= hi; j++)
+                for (int k = lo; k <= hi; k++)
+                    if (member(i, j, k)) used[level_of(i, j, k)] = 1;
+        while (nlevels > 1 && !used[nlevels - 1]) nlevels--;
+    }
+    // constrained axes: bit 0 of the part index = sign on z, bit 1 = y, bit 2 = x (0: d >= 0, 1: d <= 0)
+    const int nbits = parts == 1 ? 0 : (parts == 2 ? 1 : (parts == 4 ? 2 : 3));
+    auto in_part = [&](int part, int i, int j, int k, bool& owned) {
+        const int d[3] = {k, j, i};
+        owned = true;
+        for (int b = 0; b < nbits; b++) {
+            const bool neg = (part >> b) & 1;
+            if (neg ? d[b] > 0 : d[b] < 0) return false;
+            if (neg && d[b] == 0) owned = false;  // bounding plane: rated by the positive side only
+        }
+        return true;
+    };
+
+    plan.level_start.assign((size_t)parts * (nlevels + 1), 0);
+    plan.cells.clear();
     int maxc = 0;
-    for (int m = 0; m < nlevels; m++) {
-        plan.level_start[m + 1] = plan.level_start[m] + count[m];
-        maxc = std::max(maxc, count[m]);
-    }
-    // drop empty trailing levels (cannot happen: the octahedron tips reach every level up to min(Q, bound))
-    if (maxc > 65535) {
-        err = "sweep plan: level too large for 16-bit slots";
-        return false;
-    }
-    const int64_t total = plan.level_start[nlevels];
-    plan.cells.resize(total);
-    // pass 2: slots = rank inside the level, rated cells first, lexicographic inside each group
-    std::vector<int32_t> slot((size_t)side * side * side, -1);
+    std::vector<int32_t> slot((size_t)side * side * side);
     auto sidx = [&](int i, int j, int k) { return ((size_t)(i - lo) * side + (j - lo)) * side + (k - lo); };
-    {
-        std::vector<int> fill_rated(nlevels, 0), nrated(nlevels, 0), fill_un(nlevels, 0);
+
+    for (int part = 0; part < parts; part++) {
+        std::fill(slot.begin(), slot.end(), -1);
+        // pass 1: level sizes and slots (rank inside the level; rate-receiving cells first, then lexicographic)
+        std::vector<int> count(nlevels, 0), nfirst(nlevels, 0), fill_a(nlevels, 0), fill_b(nlevels, 0);
         for (int i = lo; i <= hi; i++)
             for (int j = lo; j <= hi; j++)
                 for (int k = lo; k <= hi; k++) {
-                    if (!member(i, j, k)) continue;
-                    if (rated(i, j, k)) nrated[std::max(std::abs(i), std::max(std::abs(j), std::abs(k)))]++;
+                    bool owned;
+                    if (!member(i, j, k) || !in_part(part, i, j, k, owned)) continue;
+                    const int m = level_of(i, j, k);
+                    count[m]++;
+                    if (owned && rated(i, j, k)) nfirst[m]++;
                 }
         for (int i = lo; i <= hi; i++)
             for (int j = lo; j <= hi; j++)
                 for (int k = lo; k <= hi; k++) {
-                    if (!member(i, j, k)) continue;
-                    int m = std::max(std::abs(i), std::max(std::abs(j), std::abs(k)));
-                    slot[sidx(i, j, k)] = rated(i, j, k) ? fill_rated[m]++ : nrated[m] + fill_un[m]++;
+                    bool owned;
+                    if (!member(i, j, k) || !in_part(part, i, j, k, owned)) continue;
+                    const int m = level_of(i, j, k);
+                    slot[sidx(i, j, k)] = (owned && rated(i, j, k)) ? fill_a[m]++ : nfirst[m] + fill_b[m]++;
+                }
+        int* ls = plan.level_start.data() + (size_t)part * (nlevels + 1);
+        ls[0] = (int)plan.cells.size();
+        for (int m = 0; m < nlevels; m++) {
+            ls[m + 1] = ls[m] + count[m];
+            maxc = std::max(maxc, count[m]);
+        }
+        if (maxc > 65535) {
+            err = "sweep plan: level too large for 16-bit slots";
+            return false;
+        }
+        plan.cells.resize((size_t)ls[nlevels]);
+        // pass 2: geometry
+        for (int i = lo; i <= hi; i++)
+            for (int j = lo; j <= hi; j++)
+                for (int k = lo; k <= hi; k++) {
+                    bool owned;
+                    if (!member(i, j, k) || !in_part(part, i, j, k, owned)) continue;
+                    const int ia = std::abs(i), ja = std::abs(j), ka = std::abs(k);
+                    const int m = level_of(i, j, k);
+                    PlanCell pc;
+                    pc.d[0] = (uint8_t)(i - lo);
+                    pc.d[1] = (uint8_t)(j - lo);
+                    pc.d[2] = (uint8_t)(k - lo);
+                    pc.pad = 0;
+                    pc.flags = 0;
+                    pc.nb[0] = pc.nb[1] = pc.nb[2] = pc.nb[3] = 0;
+                    if (m == 0) {
+                        // source cell: no incoming column, path dr/2, volume dr^3 (raytracing.cu:285-294).
+                        // wA = wB = 0 makes it "interpolate" slot 0 of the previous buffer with weight 1;
+                        // the kernel seeds that slot with 0.
+                        pc.flags = PC_SOURCE | (owned ? PC_RATED : 0u);
+                        pc.wA = pc.wB = 0.0;
+                        pc.path = 0.5;
+                        pc.inv_np = ASORA_FOURPI;
+                    } else {
+                        const int si = sign1(i), sj = sign1(j), sk = sign1(k);
+                        const int im = i - si, jm = j - sj, km = k - sk;
+                        int a, b, c;                     // |minor A|, |minor B|, |dominant|
+                        int n1[3], n2[3], n3[3], n4[3];  // upstream cells c1..c4
+                        // dominant-axis selection with the reference's tie order (raytracing.cu:394,446,491)
+                        if (ka >= ja && ka >= ia) {
+                            a = ia; b = ja; c = ka;  // A = x, B = y (raytracing.cu:416-419)
+                            n1[0] = im; n1[1] = jm; n1[2] = km;
+                            n2[0] = i;  n2[1] = jm; n2[2] = km;
+                            n3[0] = im; n3[1] = j;  n3[2] = km;
+                            n4[0] = i;  n4[1] = j;  n4[2] = km;
+                        } else if (ja >= ia && ja >= ka) {
+                            a = ia; b = ka; c = ja;  // A = x, B = z (raytracing.cu:464-467)
+                            n1[0] = im; n1[1] = jm; n1[2] = km;
+                            n2[0] = i;  n2[1] = jm; n2[2] = km;
+                            n3[0] = im; n3[1] = jm; n3[2] = k;
+                            n4[0] = i;  n4[1] = jm; n4[2] = k;
+                        } else {
+                            a = ja; b = ka; c = ia;  // A = y, B = z (raytracing.cu:509-512)
+                            n1[0] = im; n1[1] = jm; n1[2] = km;
+                            n2[0] = im; n2[1] = j;  n2[2] = km;
+                            n3[0] = im; n3[1] = jm; n3[2] = k;
+                            n4[0] = im; n4[1] = j;  n4[2] = k;
+                        }
+                        // With dx = 1 - a/c (raytracing.cu:397-403 in source-relative coordinates) the
+                        // bilinear weights are s1 = wA*wB, s2 = wB*(1-wA), s3 = wA*(1-wB), s4 = (1-wA)*(1-wB).
+                        pc.wA = (double)a / (double)c;
+                        pc.wB = (double)b / (double)c;
+                        const double da = a, db = b, dc = c;
+                        pc.path = std::sqrt((da * da + db * db) / (dc * dc) + 1.0);  // raytracing.cu:444
+                        const int n = ia * ia + ja * ja + ka * ka;
+                        pc.inv_np = 1.0 / ((double)n * pc.path);
+                        if (c == 1 && (a == 1 || b == 1)) pc.flags |= (a == 1 && b == 1) ? PC_DIAG3 : PC_DIAG2;
+                        if (owned && rated(i, j, k)) pc.flags |= PC_RATED;
+                        if (ka == m) pc.flags |= PC_ZFACE;
+                        // upstream slots; zero-weight corners may fall outside the part -> slot 0, weight 0
+                        const double s[4] = {pc.wA * pc.wB, pc.wB * (1.0 - pc.wA), pc.wA * (1.0 - pc.wB),
+                                             (1.0 - pc.wA) * (1.0 - pc.wB)};
+                        int* nn[4] = {n1, n2, n3, n4};
+                        for (int t = 0; t < 4; t++) {
+                            int sl = 0;
+                            if (s[t] != 0.0) {
+                                const int* q = nn[t];
+                                const bool in = q[0] >= lo && q[0] <= hi && q[1] >= lo && q[1] <= hi && q[2] >= lo && q[2] <= hi;
+                                const int32_t v = in ? slot[sidx(q[0], q[1], q[2])] : -1;
+                                if (v < 0 || level_of(q[0], q[1], q[2]) != m - 1) {
+                                    err = "sweep plan: internal error, upstream cell not in the previous level of its part";
+                                    return false;
+                                }
+                                sl = v;
+                            }
+                            pc.nb[t] = (uint16_t)sl;
+                        }
+                    }
+                    plan.cells[(size_t)ls[m] + slot[sidx(i, j, k)]] = pc;
                 }
     }
-    // pass 3: geometry
-    for (int i = lo; i <= hi; i++)
-        for (int j = lo; j <= hi; j++)
-            for (int k = lo; k <= hi; k++) {
-                const int ia = std::abs(i), ja = std::abs(j), ka = std::abs(k);
-                if (!member(i, j, k)) continue;
-                const int m = std::max(ia, std::max(ja, ka));
-                PlanCell pc;
-                pc.d[0] = (uint8_t)(i - lo);
-                pc.d[1] = (uint8_t)(j - lo);
-                pc.d[2] = (uint8_t)(k - lo);
-                pc.pad = 0;
-                pc.flags = 0;
-                pc.nb[0] = pc.nb[1] = pc.nb[2] = pc.nb[3] = 0;
-                if (m == 0) {
-                    // source cell: no incoming column, path dr/2, volume dr^3 (raytracing.cu:285-294).
-                    // wA = wB = 0 makes it "interpolate" slot 0 of the previous buffer with weight 1;
-                    // the kernel seeds that slot with 0.
-                    pc.flags = PC_SOURCE | PC_RATED;
-                    pc.wA = pc.wB = 0.0;
-                    pc.path = 0.5;
-                    pc.inv_np = ASORA_FOURPI;
-                } else {
-                    const int si = sign1(i), sj = sign1(j), sk = sign1(k);
-                    const int im = i - si, jm = j - sj, km = k - sk;
-                    int a, b, c;            // |minor A|, |minor B|, |dominant|
-                    int n1[3], n2[3], n3[3], n4[3];  // upstream cells c1..c4
-                    // dominant-axis selection with the reference's tie order (raytracing.cu:394,446,491)
-                    if (ka >= ja && ka >= ia) {
-                        a = ia; b = ja; c = ka;  // A = x, B = y (raytracing.cu:416-419)
-                        n1[0] = im; n1[1] = jm; n1[2] = km;
-                        n2[0] = i;  n2[1] = jm; n2[2] = km;
-                        n3[0] = im; n3[1] = j;  n3[2] = km;
-                        n4[0] = i;  n4[1] = j;  n4[2] = km;
-                    } else if (ja >= ia && ja >= ka) {
-                        a = ia; b = ka; c = ja;  // A = x, B = z (raytracing.cu:464-467)
-                        n1[0] = im; n1[1] = jm; n1[2] = km;
-                        n2[0] = i;  n2[1] = jm; n2[2] = km;
-                        n3[0] = im; n3[1] = jm; n3[2] = k;
-                        n4[0] = i;  n4[1] = jm; n4[2] = k;
-                    } else {
-                        a = ja; b = ka; c = ia;  // A = y, B = z (raytracing.cu:509-512)
-                        n1[0] = im; n1[1] = jm; n1[2] = km;
-                        n2[0] = im; n2[1] = j;  n2[2] = km;
-                        n3[0] = im; n3[1] = jm; n3[2] = k;
-                        n4[0] = im; n4[1] = j;  n4[2] = k;
-                    }
-                    // With dx = 1 - a/c (raytracing.cu:397-403 in source-relative coordinates) the
-                    // bilinear weights are s1 = wA*wB, s2 = wB*(1-wA), s3 = wA*(1-wB), s4 = (1-wA)*(1-wB).
-                    pc.wA = (double)a / (double)c;
-                    pc.wB = (double)b / (double)c;
-                    const double da = a, db = b, dc = c;
-                    pc.path = std::sqrt((da * da + db * db) / (dc * dc) + 1.0);  // raytracing.cu:444
-                    const int n = ia * ia + ja * ja + ka * ka;
-                    pc.inv_np = 1.0 / ((double)n * pc.path);
-                    if (c == 1 && (a == 1 || b == 1)) pc.flags |= (a == 1 && b == 1) ? PC_DIAG3 : PC_DIAG2;
-                    if (rated(i, j, k)) pc.flags |= PC_RATED;
-                    if (ka == m) pc.flags |= PC_ZFACE;
-                    // upstream slots; zero-weight corners may fall outside the plan -> slot 0, weight 0
-                    const double s[4] = {pc.wA * pc.wB, pc.wB * (1.0 - pc.wA), pc.wA * (1.0 - pc.wB),
-                                         (1.0 - pc.wA) * (1.0 - pc.wB)};
-                    int* nn[4] = {n1, n2, n3, n4};
-                    for (int t = 0; t < 4; t++) {
-                        int sl = 0;
-                        if (s[t] != 0.0) {
-                            const int* q = nn[t];
-                            bool in = q[0] >= lo && q[0] <= hi && q[1] >= lo && q[1] <= hi && q[2] >= lo && q[2] <= hi;
-                            int32_t v = in ? slot[sidx(q[0], q[1], q[2])] : -1;
-                            int ml = std::max(std::abs(q[0]), std::max(std::abs(q[1]), std::abs(q[2])));
-                            if (v < 0 || ml != m - 1) {
-                                err = "sweep plan: internal error, upstream cell not in previous level";
-                                return false;
-                            }
-                            sl = v;
-                        }
-                        pc.nb[t] = (uint16_t)sl;
-                    }
-                }
-                plan.cells[plan.level_start[m] + slot[sidx(i, j, k)]] = pc;
-            }
+    const int64_t total = (int64_t)plan.cells.size();
     plan.N = N;
     plan.R = R;
     plan.dr = dr;
@@ -221,6 +253,7 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_o
     plan.lo = lo;
     plan.side = side;
     plan.sphere_only = sphere_only;
+    plan.parts = parts;
     plan.ncells = total;
 
     std::vector<int4> soa(3 * (size_t)total);
@@ -231,11 +264,11 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_o
         soa[2 * total + e] = src[2];
     }
     cudaError_t e = cudaMalloc(&plan.d_cells, sizeof(int4) * soa.size());
-    if (e == cudaSuccess) e = cudaMalloc(&plan.d_level_start, sizeof(int) * (nlevels + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&plan.d_level_start, sizeof(int) * plan.level_start.size());
     if (e == cudaSuccess)
         e = cudaMemcpy(plan.d_cells, soa.data(), sizeof(int4) * soa.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess)
-        e = cudaMemcpy(plan.d_level_start, plan.level_start.data(), sizeof(int) * (nlevels + 1),
+        e = cudaMemcpy(plan.d_level_start, plan.level_start.data(), sizeof(int) * plan.level_start.size(),
                        cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         err = std::string("sweep plan upload: ") + cudaGetErrorString(e);

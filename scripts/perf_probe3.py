@@ -32,7 +32,7 @@ NumTau = 20000
 N = 256
 p.device_init(N, 64); p.photo_table_to_device(thin, thick)
 run(N, 1e4, 1, "f0"); run(N, 1e4, 4, "f0"); run(N, 1e4, 16, "f1")
-run(N, 100.0, 32, "f1"); run(N, 50.0, 128, "f1"); run(N, 50.0, 1000, "f0")
+run(N, 100.0, 32, "f1"); run(N, 50.0, 128, "f1", variant=2); run(N, 50.0, 1000, "f0", variant=2); run(N, 50.0, 1000, "f0"); run(N, 60.0, 500, "f0"); run(N, 40.0, 1000, "f0")
 run(N, 30.0, 200, "f0", variant=2); run(N, 30.0, 200, "f0", variant=1)
 run(N, 10.0, 200, "f0", variant=2)
 p.device_close()
