@@ -328,7 +328,7 @@ def main():
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(f"R{R:g}")
+            traffic = json.load(open(tpath)).get(f"R{R:g}")  # bytes per launch, ncu --set full (profiles/README.md)
         value = world * units_per_step * K / (dev_ms * 1e-3)
         line = {
             "metric": "ASORA source-cell updates/s", "value": value, "unit": "updates/s", "n_gpus": world,
@@ -347,7 +347,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "sweep_smem_kernel" if variant.value == 1 else "sweep_grid_kernel",
                          "kernel_ms": k_ms, "bytes_per_update": BYTES_PER_UPDATE, "peak_source": peak_src,
-                         "note": "fp64-pipe / latency bound, not HBM bound: see DESIGN.md and profiles/"},
+                         "traffic_unit": "bytes per launch (ncu dram__bytes_read+write)",
+                         "note": "issue/latency bound, not HBM bound (L2 hit rate 93 %): see DESIGN.md and profiles/README.md"},
             "clocks": clocks,
             "phi_checksum": phi_checksum,
         }
