@@ -239,9 +239,10 @@ __device__ __forceinline__ void fetch_cell(Fetched<S>& f, const int4* __restrict
 
 // One CTA per S sources.  Per level: every thread updates its cells (plan entry + neutral density from
 // global memory, four upstream column densities from the previous level's shared-memory buffer), then a
-// CTA barrier hands the level over.  Two latency-hiding variants were measured on B200 and dropped: an
-// explicitly software-pipelined loop that held the next cell's plan entry and neutral density in
-// registers across the barrier (30 % slower: register pressure), and prefetch.global.L1 of the next plan
+// CTA barrier hands the level over.  Three latency-hiding variants were measured on B200 and dropped, all
+// because the kernel sits exactly at the 64-register limit that 32 resident warps allow: holding the whole
+// next cell (plan entry + neutral density) in registers across the barrier (30 % slower), fetching only the
+// 16-byte offsets stream one cell ahead (10-40 % slower, spills), and prefetch.global.L1 of the next plan
 // entry (4 % slower).
 template <int S, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
