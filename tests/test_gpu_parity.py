@@ -276,3 +276,38 @@ def test_sphere_only_sweep_gives_identical_rates(libs, name, variant):
         np.testing.assert_array_equal(sph, full)  # one add per cell: bit-identical
     else:
         _assert_close(sph, full, f"{name} sphere-only", rtol=1e-13, floor=1e-15)
+
+
+def test_numsrc_prefix_of_uploaded_list(libs):
+    """do_all_sources(NumSrc) ray-traces the FIRST NumSrc uploaded sources (raytracing.cu:126), although a
+    whole-list sweep internally walks a Morton-ordered copy."""
+    oracle, p, _cabi, libasora = libs
+    from tests.fields import make_case
+    c = make_case("multi_n32")
+    _setup(libasora, c)
+    try:
+        k = 7
+        ck = dict(c, flux_flat=c["flux_flat"][:k])
+        phi, _, _ = _sweep(libasora, _cabi, ck, 0)
+    finally:
+        libasora.device_close()
+    ref, _, _ = oracle.asora_do_all_sources(c["R"], c["sig"], c["dr"], c["ndens"].ravel(), c["xh"].ravel(),
+                                            c["pos_flat"][:3 * k], c["flux_flat"][:k], c["N"], c["thin"], c["thick"],
+                                            c["minlogtau"], c["dlogtau"], c["NumTau"])
+    _assert_close(phi, ref, "prefix of the source list")
+
+
+def test_out_of_range_source_positions_wrap_periodically(libs):
+    """modulo_gpu (raytracing.cu:24,270-272): a source at i0 + N is the same source."""
+    oracle, p, _cabi, libasora = libs
+    from tests.fields import make_case
+    c = make_case("small_r5")
+    _setup(libasora, c)
+    try:
+        a, _, _ = _sweep(libasora, _cabi, c, 0)
+        shifted = (c["pos_flat"] + np.array([c["N"], -c["N"], 2 * c["N"]], dtype=np.int32)).astype(np.int32)
+        libasora.source_data_to_device(shifted, c["flux_flat"], 1)
+        b, _, _ = _sweep(libasora, _cabi, c, 0)
+    finally:
+        libasora.device_close()
+    np.testing.assert_array_equal(a, b)
