@@ -6,4 +6,6 @@ from .raytracing import do_raytracing
 from .chemistry import hydrogenODE
 from .radiation import make_tau_table, BlackBodySource, blackbody_tables
 from .utils.sourceutils import format_sources, generate_test_sources, read_test_sources
+from .c2ray_base import C2Ray, C2Ray_Test
+from .utils.logutils import printlog
 from . import evolve, raytracing, chemistry, asora_core, radiation, utils

@@ -158,3 +158,21 @@ def test_two_rank_source_sharding_over_gloo(tmp_path):
     p1 = np.load(tmp_path / "phi_1.npy")
     np.testing.assert_array_equal(p0, p1)
     np.testing.assert_allclose(p0, ref, rtol=1e-13, atol=0)
+
+
+def test_cosmology_bookkeeping():
+    """FlatLambdaCDM stand-in for astropy: the test-case time axis of the reference (zred_0 = 9, slices 10 Myr
+    apart) must give the redshift the reference's outputs are named after (xfrac_8.835.pkl) and time steps
+    equal to the requested spacing (c2ray_test.py:122-146, c2ray_base.py:147-168)."""
+    from pyc2ray_b200.cosmology import FlatLambdaCDM
+    c = FlatLambdaCDM(100.0, 0.27, 2.726, Ob0=0.044)
+    t9 = c.age(9.0)
+    z1 = c.z_at_age(t9 + 1e7 * 3.15576e7)
+    assert f"{z1:.3f}" == "8.835"
+    dt = c.lookback_time(9.0) - c.lookback_time(z1)
+    assert abs(dt / (1e7 * 3.15576e7) - 1.0) < 1e-9
+    # matter + Lambda analytic age as a sanity bound (radiation shortens it by < 0.5 % at z = 9)
+    H0 = 100 * 1e5 / 3.0856775814913673e24
+    an = 2 / (3 * H0 * np.sqrt(0.73)) * np.arcsinh(np.sqrt(0.73 / 0.27) * 0.1 ** 1.5)
+    assert 0.995 < t9 / an < 1.0
+    assert abs(c.scale_factor(9.0) - 0.1) < 1e-15

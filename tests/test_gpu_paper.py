@@ -53,3 +53,30 @@ def test_hackathon_test1_tolerance_ladder_vs_oracle():
     assert x_gpu.mean() > 0.01  # the source did ionise a bubble
     # far tighter than the reference's own ladder: fp64 end to end
     np.testing.assert_allclose(x_gpu, x_cpu, rtol=1e-8, atol=1e-14)
+
+
+def test_driver_class_runs_reference_style_script():
+    """The reference's driver pattern (test/paper_tests/test3_multisource/run_test.py:21-66) on the C2Ray_Test
+    class of this package: same calls, same known answer."""
+    import pyc2ray_b200 as pc2r
+    here = os.path.dirname(os.path.abspath(__file__))
+    sim = pc2r.C2Ray_Test(os.path.join(here, "golden", "params_test3.yml"), 128, True)
+    try:
+        zred_array = sim.generate_redshift_array(2, 1e7)
+        srcpos, srcflux = sim.read_sources(os.path.join(here, "golden", "src_test3.txt"), 5)
+        for k in range(len(zred_array) - 1):
+            zi, zf = zred_array[k], zred_array[k + 1]
+            dt = sim.set_timestep(zi, zf, 10)
+            sim.set_constant_average_density(1.0e-6, 0)
+            sim.zred = zi
+            for t in range(10):
+                sim.cosmo_evolve(dt)
+                sim.evolve3D(dt, srcflux, srcpos)
+        sim.write_output(zf)
+        assert f"{zf:.3f}" == "8.835"
+        k3 = KAT["test3_multisource_mean_x"]
+        ref = k3["pyc2ray"][k3["order"].index("Teff5e4")]
+        assert abs(sim.xh.mean() - ref) / ref < 5e-6, sim.xh.mean()
+        assert sim.phi_ion.shape == (128, 128, 128)
+    finally:
+        sim._gpu_close()
