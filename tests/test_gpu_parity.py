@@ -311,3 +311,47 @@ def test_out_of_range_source_positions_wrap_periodically(libs):
     finally:
         libasora.device_close()
     np.testing.assert_array_equal(a, b)
+
+
+def test_full_size_properties_256(libs):
+    """BASELINE-size checks (256^3, F1 fields, 1000 sources, R = 10.76) through size-independent properties:
+    additivity over source subsets, linearity in the fluxes, sphere-only == full, the grid-cooperative and the
+    shared-memory variants agree, and a spot check of 6 sources against the oracle."""
+    oracle, p, _cabi, libasora = libs
+    from tests.fields import f1_fields, tables, SIG, MPC
+    from pyc2ray_b200.utils.sourceutils import format_sources, generate_test_sources
+    N, ns, R = 256, 1000, 10.76
+    srcpos = generate_test_sources(N, ns, seed=100)
+    flux = 10 ** np.random.default_rng(3).normal(0, 0.5, size=ns)
+    ndens, xh = f1_fields(N, srcpos)
+    thin, thick, dlogtau, _ = tables("bb1e5")
+    dr = 2e20
+    pos_flat, flux_flat = format_sources(srcpos, flux)
+    c = dict(N=N, R=R, sig=SIG, dr=dr, ndens=ndens, xh=xh, thin=thin, thick=thick, minlogtau=-20.0, dlogtau=dlogtau,
+             NumTau=thin.size, pos_flat=pos_flat, flux_flat=flux_flat)
+    _setup(libasora, c)
+    try:
+        full, v, upd = _sweep(libasora, _cabi, c, 0)
+        assert v == 1 and upd == ns * 9919
+        _cabi.check(_cabi.L.asora_set_sphere_only(1))
+        sph, _, upd_s = _sweep(libasora, _cabi, c, 0)
+        _cabi.check(_cabi.L.asora_set_sphere_only(0))
+        assert upd_s == ns * 5185  # rated cells per source at R = 10.76 (SURVEY section 8)
+        _assert_close(sph, full, "sphere-only at 256^3", rtol=1e-12, floor=1e-15)
+        h = ns // 2
+        libasora.source_data_to_device(np.ascontiguousarray(pos_flat[:3 * h]), np.ascontiguousarray(flux_flat[:h]), h)
+        a, _, _ = _sweep(libasora, _cabi, dict(c, flux_flat=flux_flat[:h]), 0)
+        libasora.source_data_to_device(np.ascontiguousarray(pos_flat[3 * h:]), np.ascontiguousarray(2.0 * flux_flat[h:]), ns - h)
+        b2, _, _ = _sweep(libasora, _cabi, dict(c, flux_flat=flux_flat[h:]), 0)
+        _assert_close(a + 0.5 * b2, full, "additivity + linearity at 256^3", rtol=1e-11, floor=1e-14)
+        k = 6
+        libasora.source_data_to_device(np.ascontiguousarray(pos_flat[:3 * k]), np.ascontiguousarray(flux_flat[:k]), k)
+        ck = dict(c, flux_flat=flux_flat[:k])
+        s1, _, _ = _sweep(libasora, _cabi, ck, 1)
+        s2, _, _ = _sweep(libasora, _cabi, ck, 2)
+        _assert_close(s1, s2, "variant 1 vs 2 at 256^3", rtol=1e-11)
+    finally:
+        libasora.device_close()
+    ref, _, _ = oracle.asora_do_all_sources(R, SIG, dr, ndens.ravel(), xh.ravel(), pos_flat[:3 * k], flux_flat[:k], N, thin,
+                                            thick, -20.0, dlogtau, thin.size)
+    _assert_close(s1, ref, "256^3 spot check vs oracle")
