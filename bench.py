@@ -354,7 +354,7 @@ def main():
         }
         if eor is not None:
             line["eor_step"] = eor
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:  # the CPU baseline is reported at N = 1 only
             import oracle
             threads = oracle.max_threads()
             sample = max(threads, args.cpu_sample)
