@@ -94,6 +94,30 @@ struct SweepParams {
                               // the L2-resident scratch of the grid-cooperative variant
 };
 
+// ---- fp64 helpers shared by the device code ----------------------------------------------------------
+#ifdef __CUDACC__
+// 1/x for a normal, finite x: MUFU.RCP64H seed (>= 20 bits) + one cubic and one quadratic Newton step.
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    e = fma(e, e, e);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
+// a/b with a final residual correction (<= 1 ulp for normal operands)
+__device__ __forceinline__ double fast_div(double a, double b)
+{
+    const double r = fast_rcp(b);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+}
+
+#endif
+
 // host-side helpers implemented in sweep_plan.cu
 int asora_qmax(int N, double R);
 int64_t asora_count_cells(int N, double R);

@@ -47,20 +47,21 @@ global_pass_kernel(double dt, const double* __restrict__ ndens, const double* __
             // doric (chemistry.f90:279-311)
             const double aih0 = phi_p + de * acolh0;
             const double delth = aih0 + de * brech0;
-            const double eqxh = aih0 / delth;
+            // fast_div: MUFU.RCP64H seed + Newton + residual correction (<= 1 ulp), asora_common.cuh.  delth > 0
+            // and 1 - x > 0 are ordinary normal numbers here; the library division's slow path is never needed.
+            const double eqxh = fast_div(aih0, delth);
             const double deltht = delth * dt;
             const double ee = exp(-deltht);
             double x = (xh_p - eqxh) * ee + eqxh;
             if (x < CHEM_EPSILON) x = CHEM_EPSILON;
-            const double avg_factor = (deltht < (double)1.0e-8f) ? 1.0 : (1.0 - ee) / deltht;
+            const double avg_factor = (deltht < (double)1.0e-8f) ? 1.0 : fast_div(1.0 - ee, deltht);
             double xa = eqxh + (xh_p - eqxh) * avg_factor;
             if (xa < CHEM_EPSILON) xa = CHEM_EPSILON;
             xh_int_p = x;
             xh_av_p = xa;
             // chemistry.f90:182-189 (the temperature criterion is identically true: isothermal)
-            if (fabs((xh_av_p - prev) / (1.0 - xh_av_p)) < CHEM_MIN_FRAC_CHANGE ||
-                (1.0 - xh_av_p) < CHEM_MIN_FRAC_ATOMS)
-                break;
+            const double ya = 1.0 - xh_av_p;
+            if (ya < CHEM_MIN_FRAC_ATOMS || fabs(fast_div(xh_av_p - prev, ya)) < CHEM_MIN_FRAC_CHANGE) break;
             if (nit > 400) break;  // chemistry.f90:192
         }
         // chemistry.f90:96-104

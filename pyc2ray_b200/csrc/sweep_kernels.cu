@@ -35,26 +35,6 @@ namespace cg = cooperative_groups;
 // fp64 helpers
 // ---------------------------------------------------------------------------------------------------
 
-// 1/x for a normal, finite x: MUFU.RCP64H seed (>= 20 bits) + one cubic and one quadratic Newton step.
-__device__ __forceinline__ double fast_rcp(double x)
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    e = fma(e, e, e);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
-}
-
-// a/b with a final residual correction (<= 1 ulp for normal operands)
-__device__ __forceinline__ double fast_div(double a, double b)
-{
-    const double r = fast_rcp(b);
-    const double q = a * r;
-    return fma(fma(-b, q, a), r, q);
-}
-
 // Polynomial coefficients live in the constant bank so that DFMA reads them as c[][] operands instead of
 // materialising each 64-bit immediate with two UMOVs (6.7 % of the issued instructions in r01b).
 // log2(1+r) = r * (K[0] + K[1] r + ... + K[5] r^5), K[k] = (-1)^k / ((k+1) ln 2)

@@ -10,6 +10,12 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # A clean checkout has no binaries (they are git-ignored): build the CUDA library and the CPU oracle
+    # in-tree once, exactly as __graft_entry__.build() does.  Both are no-ops when up to date.
+    from pyc2ray_b200._build import build_native
+    build_native()
+    import oracle
+    oracle.build()
 
 
 def _has_gpu():
