@@ -51,7 +51,7 @@ struct Context {
     int64_t chem_stage_n = 0;
     // stats of the last sweep
     int variant_forced = 0;
-    int tune_S = 0, tune_block = 0, tune_regs = 0, tune_zface = 0;
+    int tune_S = 0, tune_block = 0, tune_regs = 0;
     int tune_parts = 0;
     int sphere_only = 0;
     // cached rated-cell count (sphere-only statistics)
@@ -92,10 +92,8 @@ int ensure_buffer(int which)
 {
     if (which < 0 || which >= ASORA_BUF_COUNT) return fail("unknown buffer id");
     if (!g.buf[which]) {
-        // the rate grid is followed by the transposed accumulator of the z-face cells (sweep_kernels.cu)
-        const size_t n = (which == ASORA_BUF_PHI_ION ? 2 : 1) * (size_t)g.ncell;
-        CK(cudaMalloc(&g.buf[which], sizeof(double) * n));
-        CK(cudaMemsetAsync(g.buf[which], 0, sizeof(double) * n, g.stream));
+        CK(cudaMalloc(&g.buf[which], sizeof(double) * g.ncell));
+        CK(cudaMemsetAsync(g.buf[which], 0, sizeof(double) * g.ncell, g.stream));
     }
     return 0;
 }
@@ -121,7 +119,7 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     if (int rc = ensure_buffer(ASORA_BUF_XH_AV)) return rc;
     if (int rc = ensure_buffer(ASORA_BUF_PHI_ION)) return rc;
     const int N = g.N;
-    if (!g.nhi) CK(cudaMalloc(&g.nhi, sizeof(double) * 2 * g.ncell));
+    if (!g.nhi) CK(cudaMalloc(&g.nhi, sizeof(double) * g.ncell));
     if (!g.log2_tab) {
         double h[512];
         host_log2_table(h);
@@ -226,26 +224,6 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     }
     if (variant == 0) variant = plan_ok ? 1 : 2;
 
-    // Transposed copies for the z-face cells: worth two extra N^3 passes (~0.25 ms at 256^3) once the sweep
-    // itself is a few milliseconds.  Not for the debug path (column densities are stored by cell index).
-    // (Measured on B200: the transposed path lowers the L1 wavefront load from 82 % to 67 % but not the run
-    // time, profiles/r01d_*; it is therefore off unless forced through asora_set_tuning.)
-    bool zface = false;
-    if (g.tune_zface == 1) zface = (variant == 1) && !coldens_grid && (2.0 * (double)g.ncell < 4294967296.0);
-    if (g.tune_zface == 2) zface = false;
-    p.zface_offset = zface ? (unsigned)g.ncell : 0u;
-    // timed region (asora_last_sweep_stats: kernel_ms): nHI pre-pass, rate-grid zeroing, sweep, z-face merge
-    CK(cudaEventRecord(g.ev0, g.stream));
-    {
-        cudaError_t e = zface ? launch_prepare_nhi_transposed(g.buf[ASORA_BUF_NDENS], g.buf[ASORA_BUF_XH_AV], g.nhi,
-                                                              g.nhi + g.ncell, N, g.stream)
-                              : launch_prepare_nhi(g.buf[ASORA_BUF_NDENS], g.buf[ASORA_BUF_XH_AV], g.nhi, g.ncell, g.stream);
-        if (e != cudaSuccess) return fail_cuda("prepare_nhi_kernel launch", e);
-        g.last_launches += 1;
-    }
-    if (zero_phi) CK(cudaMemsetAsync(g.buf[ASORA_BUF_PHI_ION], 0, sizeof(double) * g.ncell, g.stream));
-    if (zface) CK(cudaMemsetAsync(g.buf[ASORA_BUF_PHI_ION] + g.ncell, 0, sizeof(double) * g.ncell, g.stream));
-
     // host-side preparation of the grid-cooperative sweep (kept outside the timed region)
     int groups = 1;
     if (variant == 2) {
@@ -263,7 +241,6 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
                 if (g.grid_scratch) cudaFree(g.grid_scratch);
                 g.grid_scratch = nullptr;
                 g.grid_scratch_groups = 0;
-    g.grid_max_groups = 0;
                 CK(cudaMalloc(&g.grid_scratch, per * groups));
                 g.grid_scratch_groups = groups;
             }
@@ -272,6 +249,15 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
         if (!g.grid_counters) CK(cudaMalloc(&g.grid_counters, sizeof(unsigned) * 16));
     }
 
+    // timed region (asora_last_sweep_stats: kernel_ms): nHI pre-pass, rate-grid zeroing, sweep
+    CK(cudaEventRecord(g.ev0, g.stream));
+    {
+        cudaError_t e = launch_prepare_nhi(g.buf[ASORA_BUF_NDENS], g.buf[ASORA_BUF_XH_AV], g.nhi, g.ncell, g.stream);
+        if (e != cudaSuccess) return fail_cuda("prepare_nhi_kernel launch", e);
+        g.last_launches += 1;
+    }
+    if (zero_phi) CK(cudaMemsetAsync(g.buf[ASORA_BUF_PHI_ION], 0, sizeof(double) * g.ncell, g.stream));
+
     if (variant == 1) {
         g.last_levels = g.plan.nlevels;
         cudaError_t e = launch_sweep_smem(g.plan, p, S, block, g.tune_regs, g.stream, &g.last_launches);
@@ -279,11 +265,6 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     } else {
         cudaError_t e = launch_sweep_grid(p, groups, g.grid_counters, g.stream, &g.last_launches, &g.last_levels);
         if (e != cudaSuccess) return fail_cuda("sweep_grid_kernel launch", e);
-    }
-    if (zface) {
-        cudaError_t e = launch_merge_phi_transposed(g.buf[ASORA_BUF_PHI_ION], g.buf[ASORA_BUF_PHI_ION] + g.ncell, N, g.stream);
-        if (e != cudaSuccess) return fail_cuda("merge_phi_transposed_kernel launch", e);
-        g.last_launches += 1;
     }
     CK(cudaEventRecord(g.ev1, g.stream));
     g.last_variant = variant;
@@ -349,6 +330,7 @@ int asora_device_close(void)
     g.grid_scratch = nullptr;
     g.grid_counters = nullptr;
     g.grid_scratch_groups = 0;
+    g.grid_max_groups = 0;
     if (g.log2_tab) cudaFree(g.log2_tab);
     g.nhi = nullptr;
     g.log2_tab = nullptr;
@@ -629,7 +611,6 @@ int asora_set_tuning(int sources_per_cta, int block_threads)
 {
     // bit 16 of block_threads selects the relaxed register mode (profiling knob)
     g.tune_regs = (block_threads >> 16) & 1;
-    g.tune_zface = (block_threads >> 17) & 3;  // bits 17-18: 1 = force the transposed z-face path, 2 = forbid it
     g.tune_parts = (block_threads >> 20) & 15; // bits 20-23: parts per source (1, 2, 4, 8), 0 = automatic
     block_threads &= 0xffff;
     if (!(sources_per_cta == 0 || sources_per_cta == 1 || sources_per_cta == 2 || sources_per_cta == 4))

@@ -29,9 +29,6 @@
 #define PC_SOURCE 2u  // the source cell itself (raytracing.cu:285-294)
 #define PC_DIAG2 4u   // incoming column scaled by sqrt(2) (raytracing.cu:431-441)
 #define PC_DIAG3 8u   // incoming column scaled by sqrt(3)
-#define PC_ZFACE 16u  // |dk| equals the level: the cell lies on a z face, where neighbouring cells of a warp
-                      // differ in j (stride N doubles).  Such cells may be routed to the transposed copies of
-                      // nhi / phi_ion (index k*N*N + i*N + j) so that their loads and reductions coalesce too.
 
 // One cell of the sweep plan (48 bytes, three 16-byte loads).
 struct __align__(16) PlanCell {
@@ -79,10 +76,8 @@ struct SweepParams {
     double minlogtau, dlogtau;
     int NumTau;               // index clamp as passed by the caller (rates.cu:78-79)
     int ntab;                 // uploaded table length
-    const double* nhi;        // ndens * (1 - xh_av), refreshed before every sweep (raytracing.cu:275-276);
-                              // followed, when zface_offset != 0, by its (k,i,j)-ordered transpose
-    double* phi_ion;          // rate grid; followed, when zface_offset != 0, by the transposed accumulator
-    unsigned zface_offset;    // 0, or N^3: element offset of the transposed copies
+    const double* nhi;        // ndens * (1 - xh_av), refreshed before every sweep (raytracing.cu:275-276)
+    double* phi_ion;
     const double2* thin;      // {T[i], T[i+1]-T[i]} pairs of the uploaded tables
     const double2* thick;
     const double2* log2_tab;  // 256 x {1/c_j, log2 c_j}, c_j the centre of mantissa bin j
@@ -134,9 +129,6 @@ cudaError_t launch_sweep_grid(const SweepParams& p, int ngroups, unsigned* count
                               int* launches, int* levels);
 
 cudaError_t launch_prepare_nhi(const double* ndens, const double* xh_av, double* nhi, int64_t ncell, cudaStream_t stream);
-cudaError_t launch_prepare_nhi_transposed(const double* ndens, const double* xh_av, double* nhi, double* nhi_t, int N,
-                                          cudaStream_t stream);
-cudaError_t launch_merge_phi_transposed(double* phi, const double* phi_t, int N, cudaStream_t stream);
 cudaError_t launch_pair_table(const double* table, double2* pairs, int ntab, cudaStream_t stream);
 void host_log2_table(double* tab512);
 

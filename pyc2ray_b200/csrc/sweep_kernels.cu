@@ -206,13 +206,10 @@ __device__ __forceinline__ void fetch_cell(Fetched<S>& f, const int4* __restrict
     f.nb4 = (unsigned)r2.y >> 16;
     const unsigned di = r2.z & 0xff, dj = (r2.z >> 8) & 0xff, dk = (r2.z >> 16) & 0xff;
     f.flags = ((unsigned)r2.z >> 24) & 0xffu;
-    // z-face cells use the second set of wrap tables (transposed strides + offset of the transposed grids
-    // when those are in use, a copy of the first set otherwise)
-    const unsigned* wz = wrap_tab + ((f.flags & PC_ZFACE) ? 3 * S * side : 0);
 #pragma unroll
     for (int s = 0; s < S; s++) {
-        const unsigned* w = wz + 3 * s * side;
-        f.pos[s] = w[di] + w[side + dj] + w[2 * side + dk];  // < 2 N^3 <= 2^32
+        const unsigned* w = wrap_tab + 3 * s * side;
+        f.pos[s] = w[di] + w[side + dj] + w[2 * side + dk];  // N <= 1600: fits 32 bits
         f.nhi[s] = __ldg(nhi + f.pos[s]);
     }
 }
@@ -232,7 +229,7 @@ sweep_smem_kernel(const int4* __restrict__ plan, int ncells, const int* __restri
     extern __shared__ double2 sh_raw[];
     double2* log2_tab = sh_raw;                                 // 256 entries
     double* sh_cd = reinterpret_cast<double*>(sh_raw + 256);    // [2][S][max_level_cells]
-    unsigned* wrap_tab = reinterpret_cast<unsigned*>(sh_cd + (size_t)2 * S * max_level_cells);  // [2][S][3][side]
+    unsigned* wrap_tab = reinterpret_cast<unsigned*>(sh_cd + (size_t)2 * S * max_level_cells);  // [S][3][side]
     const int N = p.N;
     // CTA -> (group of S sources, part of the sweep)
     const int part = blockIdx.x % parts;
@@ -260,14 +257,8 @@ sweep_smem_kernel(const int4* __restrict__ plan, int ncells, const int* __restri
         for (int t = threadIdx.x; t < 3 * side; t += BLOCK) {
             const int axis = t / side, d = t - axis * side + lo;
             const int c0 = axis == 0 ? i0[s] : (axis == 1 ? j0[s] : k0[s]);
-            const unsigned w = (unsigned)wrap(c0 + d, N);
-            const unsigned NN = (unsigned)N * N;
-            const unsigned stride = axis == 0 ? NN : (axis == 1 ? (unsigned)N : 1u);
-            // transposed layout (k,i,j): i*N + j + k*N*N, plus the offset of the transposed grids (on x)
-            const unsigned stride_t = axis == 0 ? (unsigned)N : (axis == 1 ? 1u : NN);
-            wrap_tab[3 * s * side + t] = w * stride;
-            wrap_tab[3 * S * side + 3 * s * side + t] =
-                p.zface_offset ? w * stride_t + (axis == 0 ? p.zface_offset : 0u) : w * stride;
+            const unsigned stride = axis == 0 ? (unsigned)N * N : (axis == 1 ? (unsigned)N : 1u);
+            wrap_tab[3 * s * side + t] = (unsigned)wrap(c0 + d, N) * stride;
         }
     __syncthreads();
 
@@ -296,7 +287,7 @@ sweep_smem_kernel(const int4* __restrict__ plan, int ncells, const int* __restri
 size_t sweep_smem_bytes(const SweepPlan& plan, int S)
 {
     return 256 * sizeof(double2) + (size_t)2 * S * plan.max_level_cells * sizeof(double) +
-           (size_t)2 * 3 * S * plan.side * sizeof(unsigned);
+           (size_t)3 * S * plan.side * sizeof(unsigned);
 }
 
 template <int S, int BLOCK, int MINB>
@@ -540,62 +531,6 @@ cudaError_t launch_prepare_nhi(const double* ndens, const double* xh_av, double*
     int64_t blocks = (ncell + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     prepare_nhi_kernel<<<(int)blocks, 256, 0, stream>>>(ndens, xh_av, nhi, ncell);
-    return cudaGetLastError();
-}
-
-// Same, plus the (k,i,j)-ordered transpose nhi_t[k*N*N + i*N + j] through a 32x32 shared-memory tile, so that
-// both grids are written with coalesced stores.
-__global__ void prepare_nhi_transposed_kernel(const double* __restrict__ ndens, const double* __restrict__ xh_av,
-                                              double* __restrict__ nhi, double* __restrict__ nhi_t, int N)
-{
-    __shared__ double tile[32][33];
-    const int i = blockIdx.z;
-    const int j0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        const int j = j0 + r, k = k0 + threadIdx.x;
-        if (j < N && k < N) {
-            const size_t idx = ((size_t)i * N + j) * N + k;
-            const double v = ndens[idx] * (1.0 - xh_av[idx]);
-            nhi[idx] = v;
-            tile[r][threadIdx.x] = v;
-        }
-    }
-    __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        const int k = k0 + r, j = j0 + threadIdx.x;
-        if (j < N && k < N) nhi_t[((size_t)k * N + i) * N + j] = tile[threadIdx.x][r];
-    }
-}
-
-cudaError_t launch_prepare_nhi_transposed(const double* ndens, const double* xh_av, double* nhi, double* nhi_t, int N,
-                                          cudaStream_t stream)
-{
-    dim3 grid((N + 31) / 32, (N + 31) / 32, N), block(32, 8);
-    prepare_nhi_transposed_kernel<<<grid, block, 0, stream>>>(ndens, xh_av, nhi, nhi_t, N);
-    return cudaGetLastError();
-}
-
-// phi[i][j][k] += phi_t[k][i][j]: folds the rates accumulated for z-face cells back into the rate grid.
-__global__ void merge_phi_transposed_kernel(double* __restrict__ phi, const double* __restrict__ phi_t, int N)
-{
-    __shared__ double tile[32][33];
-    const int i = blockIdx.z;
-    const int j0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        const int k = k0 + r, j = j0 + threadIdx.x;
-        if (j < N && k < N) tile[r][threadIdx.x] = phi_t[((size_t)k * N + i) * N + j];
-    }
-    __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        const int j = j0 + r, k = k0 + threadIdx.x;
-        if (j < N && k < N) phi[((size_t)i * N + j) * N + k] += tile[threadIdx.x][r];
-    }
-}
-
-cudaError_t launch_merge_phi_transposed(double* phi, const double* phi_t, int N, cudaStream_t stream)
-{
-    dim3 grid((N + 31) / 32, (N + 31) / 32, N), block(32, 8);
-    merge_phi_transposed_kernel<<<grid, block, 0, stream>>>(phi, phi_t, N);
     return cudaGetLastError();
 }
 

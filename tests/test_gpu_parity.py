@@ -355,3 +355,24 @@ def test_full_size_properties_256(libs):
     ref, _, _ = oracle.asora_do_all_sources(R, SIG, dr, ndens.ravel(), xh.ravel(), pos_flat[:3 * k], flux_flat[:k], N, thin,
                                             thick, -20.0, dlogtau, thin.size)
     _assert_close(s1, ref, "256^3 spot check vs oracle")
+
+
+def test_do_raytracing_wrapper(libs):
+    """pyc2ray_b200.do_raytracing (pyc2ray/raytracing.py:34-108): 1-indexed (3,Ns) sources, 3-D grids in any
+    memory order, returns phi_ion of shape (N,N,N)."""
+    oracle, p, _cabi, libasora = libs
+    from tests.fields import make_case
+    c = make_case("multi_n32")
+    N = c["N"]
+    p.device_init(N, 8)
+    try:
+        p.photo_table_to_device(c["thin"], c["thick"])
+        phi, heat = p.do_raytracing(c["dr"], c["flux"], c["srcpos"], True, 1000, 64, 1e-2, np.asfortranarray(c["ndens"]),
+                                    np.asfortranarray(c["xh"]), c["thin"], c["thick"], None, None, c["minlogtau"],
+                                    c["dlogtau"], c["R"], c["sig"], logfile=None, quiet=True)
+    finally:
+        p.device_close()
+    ref, _, _ = oracle.asora_do_all_sources(c["R"], c["sig"], c["dr"], c["ndens"].ravel(), c["xh"].ravel(), c["pos_flat"],
+                                            c["flux_flat"], N, c["thin"], c["thick"], c["minlogtau"], c["dlogtau"], c["NumTau"])
+    assert phi.shape == (N, N, N) and heat is None
+    _assert_close(phi.ravel(), ref, "do_raytracing")
