@@ -376,3 +376,26 @@ def test_do_raytracing_wrapper(libs):
                                             c["flux_flat"], N, c["thin"], c["thick"], c["minlogtau"], c["dlogtau"], c["NumTau"])
     assert phi.shape == (N, N, N) and heat is None
     _assert_close(phi.ravel(), ref, "do_raytracing")
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_degenerate_inputs(libs, variant):
+    """Empty source list -> phi_ion is all zeros; R below one cell -> only cells with dist <= R are rated."""
+    oracle, p, _cabi, libasora = libs
+    from tests.fields import make_case
+    c = make_case("small_r5")
+    _setup(libasora, c)
+    try:
+        c0 = dict(c, flux_flat=c["flux_flat"][:0])
+        phi, _, upd = _sweep(libasora, _cabi, c0, variant)
+        assert upd == 0 and not phi.any()
+        for R in (0.0, 0.5, 1.0, 1.5):
+            cr = dict(c, R=R)
+            phi, _, upd = _sweep(libasora, _cabi, cr, variant)
+            ref, _, n = oracle.asora_do_all_sources(R, c["sig"], c["dr"], c["ndens"].ravel(), c["xh"].ravel(), c["pos_flat"],
+                                                    c["flux_flat"], c["N"], c["thin"], c["thick"], c["minlogtau"],
+                                                    c["dlogtau"], c["NumTau"])
+            assert upd == n
+            _assert_close(phi, ref, f"R={R}")
+    finally:
+        libasora.device_close()
