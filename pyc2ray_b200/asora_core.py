@@ -1,40 +1,45 @@
-"""Initialisation state of the ASORA library (reference: pyc2ray/asora_core.py)."""
+"""Device life-cycle of the ASORA library as pyc2ray exposes it (reference: pyc2ray/asora_core.py:14-58):
+``device_init`` / ``device_close`` / ``photo_table_to_device`` plus the ``cuda_is_init`` guard the evolve and
+ray-tracing entry points check before touching the GPU."""
 from .load_extensions import load_asora
-
-libasora = load_asora()
 
 __all__ = ["cuda_is_init", "device_init", "device_close", "photo_table_to_device"]
 
-cuda_init = False
+libasora = load_asora()
+_NOT_INIT = "GPU not initialized. Please initialize it by calling device_init(N)"  # asora_core.py:47,58
+
+
+class _DeviceState:
+    ready = False
 
 
 def cuda_is_init():
-    return cuda_init
+    """True between device_init() and device_close()."""
+    return _DeviceState.ready
+
+
+def _require_device():
+    if not _DeviceState.ready:
+        raise RuntimeError(_NOT_INIT)
 
 
 def device_init(N, source_batch_size):
-    """Initialise the GPU and allocate the grids for mesh size N (asora_core.py:20-37).
-
-    ``source_batch_size`` is kept for compatibility; column densities stay on-chip here, so it does
-    not bound memory any more."""
-    global cuda_init
-    if libasora is None:
-        raise RuntimeError("Could not initialize GPU: ASORA library not loaded")
+    """Bind to the current CUDA device and allocate the grids for an N^3 mesh (asora_core.py:20-37).
+    ``source_batch_size`` is accepted for compatibility: column densities stay on-chip here, so it no longer
+    bounds memory use."""
     libasora.device_init(N, source_batch_size)
-    cuda_init = True
+    _DeviceState.ready = True
 
 
 def device_close():
-    """asora_core.py:39-47"""
-    global cuda_init
-    if not cuda_init:
-        raise RuntimeError("GPU not initialized. Please initialize it by calling device_init(N)")
+    """Free all device memory (asora_core.py:39-47)."""
+    _require_device()
     libasora.device_close()
-    cuda_init = False
+    _DeviceState.ready = False
 
 
 def photo_table_to_device(thin_table, thick_table):
-    """asora_core.py:49-58"""
-    if not cuda_init:
-        raise RuntimeError("GPU not initialized. Please initialize it by calling device_init(N)")
+    """Upload the optically thin / thick photo-ionisation tables (asora_core.py:49-58); the table length is
+    taken from ``thin_table``, as in the reference."""
+    _require_device()
     libasora.photo_table_to_device(thin_table, thick_table, thin_table.shape[0])

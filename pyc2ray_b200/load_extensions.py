@@ -1,29 +1,25 @@
-"""Loader for the two extension modules (reference: pyc2ray/load_extensions.py:9-47).
+"""Access to the two extension modules of the boundary, imported once and cached.
 
-The reference falls back to CPU-only operation when libasora is missing (:41-44); this build has no
-CPU path, so a missing CUDA library is an error."""
+Same entry points as the reference (pyc2ray/load_extensions.py:9-47: ``load_c2ray``, ``load_asora``), different
+policy: the reference degrades to CPU-only operation when libasora cannot be imported (:41-44); this build has
+no CPU path, so an unusable CUDA library is a RuntimeError that names the cause."""
+import functools
+import importlib
 
-_c2ray_lib = None
-_asora_lib = None
+
+@functools.lru_cache(maxsize=None)
+def _load(name, what):
+    try:
+        return importlib.import_module(f"{__package__}.lib.{name}")
+    except ImportError as exc:
+        raise RuntimeError(f"Could not load {what} library ({exc}); there is no CPU fallback in this build") from exc
 
 
 def load_c2ray():
-    global _c2ray_lib
-    if _c2ray_lib is None:
-        try:
-            from .lib import libc2ray
-        except ImportError as e:
-            raise RuntimeError(f"Could not load c2ray library ({e})")
-        _c2ray_lib = libc2ray
-    return _c2ray_lib
+    """Chemistry half of the boundary (stands in for the f2py module libc2ray)."""
+    return _load("libc2ray", "c2ray")
 
 
 def load_asora():
-    global _asora_lib
-    if _asora_lib is None:
-        try:
-            from .lib import libasora
-        except ImportError as e:
-            raise RuntimeError(f"Could not load ASORA library ({e}); there is no CPU fallback in this build")
-        _asora_lib = libasora
-    return _asora_lib
+    """Ray-tracing half of the boundary (stands in for the CPython module libasora)."""
+    return _load("libasora", "ASORA")
