@@ -54,10 +54,14 @@ struct Context {
     int tune_S = 0, tune_block = 0, tune_regs = 0;
     int tune_parts = 0;
     int sphere_only = 0;
-    // cached rated-cell count (sphere-only statistics)
-    int rated_N = 0;
-    double rated_R = 0, rated_dr = 0;
-    int64_t rated_cells = 0;
+    // parameters of the last sweep, for the lazily evaluated update count; and a one-entry cache of it
+    int last_count = 0;
+    double last_R = 0, last_dr = 0;
+    bool last_sphere_only = false;
+    int cells_N = 0;
+    double cells_R = 0, cells_dr = 0;
+    bool cells_sphere_only = false;
+    int64_t cells_per_source = 0;
     int last_variant = 0, last_launches = 0, last_qmax = 0, last_levels = 0;
     int64_t last_updates = 0;
     float last_ms = 0.f;
@@ -163,17 +167,12 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
 
     g.last_qmax = p.q_max;
     g.last_launches = 0;
-    if (sphere_only) {
-        if (!(g.rated_N == N && g.rated_R == R && g.rated_dr == dr)) {
-            g.rated_cells = asora_count_rated_cells(N, R, dr);
-            g.rated_N = N;
-            g.rated_R = R;
-            g.rated_dr = dr;
-        }
-        g.last_updates = (int64_t)count * g.rated_cells;
-    } else {
-        g.last_updates = (int64_t)count * asora_count_cells(N, R);
-    }
+    // the update count of this sweep is evaluated lazily (asora_last_sweep_stats): counting cells is O(side^3)
+    g.last_count = count;
+    g.last_R = R;
+    g.last_dr = dr;
+    g.last_sphere_only = sphere_only;
+    g.last_updates = -1;
     g.last_ms = 0.f;
 
     // Variant selection: the shared-memory sweep needs two levels of column densities per source.
@@ -331,6 +330,7 @@ int asora_device_close(void)
     g.grid_counters = nullptr;
     g.grid_scratch_groups = 0;
     g.grid_max_groups = 0;
+    g.cells_N = 0;
     if (g.log2_tab) cudaFree(g.log2_tab);
     g.nhi = nullptr;
     g.log2_tab = nullptr;
@@ -625,7 +625,21 @@ int asora_last_sweep_stats(int* variant, int* launches, int64_t* updates, int* q
 {
     if (variant) *variant = g.last_variant;
     if (launches) *launches = g.last_launches;
-    if (updates) *updates = g.last_updates;
+    if (updates) {
+        if (g.last_updates < 0) {
+            if (!(g.cells_N == g.N && g.cells_R == g.last_R && g.cells_sphere_only == g.last_sphere_only &&
+                  (!g.last_sphere_only || g.cells_dr == g.last_dr))) {
+                g.cells_per_source = g.last_sphere_only ? asora_count_rated_cells(g.N, g.last_R, g.last_dr)
+                                                        : asora_count_cells(g.N, g.last_R);
+                g.cells_N = g.N;
+                g.cells_R = g.last_R;
+                g.cells_dr = g.last_dr;
+                g.cells_sphere_only = g.last_sphere_only;
+            }
+            g.last_updates = (int64_t)g.last_count * g.cells_per_source;
+        }
+        *updates = g.last_updates;
+    }
     if (q_max) *q_max = g.last_qmax;
     if (levels) *levels = g.last_levels;
     if (kernel_ms) *kernel_ms = g.last_ms;
