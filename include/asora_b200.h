@@ -111,6 +111,18 @@ int asora_raytrace_device(double R, double sig, double dr, int src_begin, int sr
 int asora_global_pass_device(double dt, double bh00, double albpow, double colh0, double temph0,
                              double abu_c, int* conv_flag, double* sum_xh1, double* sum_xh0);
 
+/* Slab-decomposed multi-GPU runs (pyc2ray_b200/evolve.py, decomposition="slab").  The planes i in
+ * [x_begin, x_begin + x_count) (periodic in N) are the only ones the following sweeps of this rank can touch
+ * (its sources plus the ray-tracing radius): the nHI pre-pass and the zeroing of PHI_ION are restricted to
+ * them.  x_count >= N (or 0) restores the whole grid. */
+int asora_set_active_slab(int x_begin, int x_count);
+
+/* asora_global_pass_device restricted to cells [cell_offset, cell_offset + cell_count) of the flat grids
+ * (one rank's own planes: cell_offset = x * N * N). */
+int asora_global_pass_device_range(double dt, double bh00, double albpow, double colh0, double temph0,
+                                   double abu_c, int64_t cell_offset, int64_t cell_count, int* conv_flag,
+                                   double* sum_xh1, double* sum_xh0);
+
 /* Wait for all work queued on the context's stream. */
 int asora_sync(void);
 

@@ -53,6 +53,7 @@ struct Context {
     int variant_forced = 0;
     int tune_S = 0, tune_block = 0, tune_regs = 0;
     int tune_parts = 0;
+    int slab_begin = 0, slab_count = 0;  // active planes of a slab-decomposed run (0 = whole grid)
     int sphere_only = 0;
     // parameters of the last sweep, for the lazily evaluated update count; and a one-entry cache of it
     int last_count = 0;
@@ -251,11 +252,27 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     // timed region (asora_last_sweep_stats: kernel_ms): nHI pre-pass, rate-grid zeroing, sweep
     CK(cudaEventRecord(g.ev0, g.stream));
     {
-        cudaError_t e = launch_prepare_nhi(g.buf[ASORA_BUF_NDENS], g.buf[ASORA_BUF_XH_AV], g.nhi, g.ncell, g.stream);
-        if (e != cudaSuccess) return fail_cuda("prepare_nhi_kernel launch", e);
-        g.last_launches += 1;
+        // whole grid, or the (periodic) range of planes this rank's sweeps can touch: at most two segments
+        const int64_t plane = (int64_t)N * N;
+        int64_t seg_off[2] = {0, 0}, seg_len[2] = {g.ncell, 0};
+        if (g.slab_count > 0 && g.slab_count < N) {
+            const int b = ((g.slab_begin % N) + N) % N;
+            const int first = std::min(g.slab_count, N - b);
+            seg_off[0] = b * plane;
+            seg_len[0] = first * plane;
+            seg_off[1] = 0;
+            seg_len[1] = (g.slab_count - first) * plane;
+        }
+        for (int sg = 0; sg < 2; sg++) {
+            if (seg_len[sg] <= 0) continue;
+            cudaError_t e = launch_prepare_nhi(g.buf[ASORA_BUF_NDENS] + seg_off[sg], g.buf[ASORA_BUF_XH_AV] + seg_off[sg],
+                                               g.nhi + seg_off[sg], seg_len[sg], g.stream);
+            if (e != cudaSuccess) return fail_cuda("prepare_nhi_kernel launch", e);
+            g.last_launches += 1;
+            if (zero_phi)
+                CK(cudaMemsetAsync(g.buf[ASORA_BUF_PHI_ION] + seg_off[sg], 0, sizeof(double) * seg_len[sg], g.stream));
+        }
     }
-    if (zero_phi) CK(cudaMemsetAsync(g.buf[ASORA_BUF_PHI_ION], 0, sizeof(double) * g.ncell, g.stream));
 
     if (variant == 1) {
         g.last_levels = g.plan.nlevels;
@@ -331,6 +348,7 @@ int asora_device_close(void)
     g.grid_scratch_groups = 0;
     g.grid_max_groups = 0;
     g.cells_N = 0;
+    g.slab_begin = g.slab_count = 0;
     if (g.log2_tab) cudaFree(g.log2_tab);
     g.nhi = nullptr;
     g.log2_tab = nullptr;
@@ -522,6 +540,42 @@ int asora_buffer_download(int which, double* host)
     if (int rc = ensure_buffer(which)) return rc;
     CK(cudaMemcpyAsync(host, g.buf[which], sizeof(double) * g.ncell, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+int asora_set_active_slab(int x_begin, int x_count)
+{
+    if (int rc = need_init()) return rc;
+    if (x_count < 0) return fail("set_active_slab: negative plane count");
+    g.slab_begin = x_begin;
+    g.slab_count = (x_count >= g.N) ? 0 : x_count;
+    return 0;
+}
+
+int asora_global_pass_device_range(double dt, double bh00, double albpow, double colh0, double temph0, double abu_c,
+                                   int64_t cell_offset, int64_t cell_count, int* conv_flag, double* sum_xh1,
+                                   double* sum_xh0)
+{
+    if (int rc = need_init()) return rc;
+    if (cell_offset < 0 || cell_count < 0 || cell_offset + cell_count > g.ncell)
+        return fail("global_pass_device_range: range outside the grid");
+    const int ids[] = {ASORA_BUF_NDENS, ASORA_BUF_TEMP, ASORA_BUF_XH, ASORA_BUF_XH_AV, ASORA_BUF_XH_INTERMED,
+                       ASORA_BUF_PHI_ION};
+    for (int id : ids)
+        if (int rc = ensure_buffer(id)) return rc;
+    if (int rc = ensure_chem_scratch()) return rc;
+    if (cell_count == 0) {
+        if (conv_flag) *conv_flag = 0;
+        if (sum_xh1) *sum_xh1 = 0.0;
+        if (sum_xh0) *sum_xh0 = 0.0;
+        return 0;
+    }
+    const int64_t o = cell_offset;
+    cudaError_t e = launch_global_pass(dt, g.buf[ASORA_BUF_NDENS] + o, g.buf[ASORA_BUF_TEMP] + o, g.buf[ASORA_BUF_XH] + o,
+                                       g.buf[ASORA_BUF_XH_AV] + o, g.buf[ASORA_BUF_XH_INTERMED] + o,
+                                       g.buf[ASORA_BUF_PHI_ION] + o, bh00, albpow, colh0, temph0, abu_c, cell_count, 1,
+                                       g.chem_partials, g.chem_iparts, g.chem_blocks, conv_flag, sum_xh1, sum_xh0, g.stream);
+    if (e != cudaSuccess) return fail_cuda("global_pass_kernel", e);
     return 0;
 }
 

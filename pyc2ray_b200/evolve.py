@@ -14,7 +14,7 @@ import numpy as np
 from .asora_core import cuda_is_init
 from .lib import _cabi
 from .lib._cabi import L, check, dptr, iptr
-from .parallel import shard_bounds, allreduce_sum_, device_tensor
+from .parallel import shard_bounds, allreduce_sum_, device_tensor, slab_edges, SlabHalo
 from .utils import printlog
 from .utils.sourceutils import format_sources
 
@@ -29,7 +29,7 @@ def _flat(a):
 
 def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table, minlogtau, dlogtau, R_max_LLS,
                    convergence_fraction, sig, bh00, albpow, colh0, temph0, abu_c, logfile, quiet, shard=None,
-                   group=None, max_iter=10000):
+                   group=None, max_iter=10000, decomposition="list"):
     if not cuda_is_init():
         raise RuntimeError("GPU not initialized. Please initialize it by calling device_init(N)")
     NumSrc_total = src_flux.shape[0]
@@ -40,10 +40,23 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
     prev_sum_xh1_int = 2 * NumCells
     prev_sum_xh0_int = 2 * NumCells
 
+    halo = None
     if shard is not None:
         rank, nprocs = shard
-        i_start, i_end = shard_bounds(NumSrc_total, rank, nprocs)
-        srcpos_flat, normflux_flat = format_sources(src_pos[:, i_start:i_end], src_flux[i_start:i_end])
+        edges = None
+        if decomposition in ("auto", "slab"):
+            # shard by position: planes of the slowest axis with equal source counts (parallel.py)
+            edges, h = slab_edges(np.asarray(src_pos)[0] - 1, N, nprocs, R_max_LLS)
+            if edges is None and decomposition == "slab":
+                raise ValueError("slab decomposition impossible: a slab would be thinner than two halos")
+        if edges is not None:
+            halo = SlabHalo(edges, h, N, rank, nprocs, group)
+            x0 = np.mod(np.asarray(src_pos)[0].astype(np.int64) - 1, N)
+            mine = (x0 >= halo.lo) & (x0 < halo.hi)
+            srcpos_flat, normflux_flat = format_sources(np.asarray(src_pos)[:, mine], np.asarray(src_flux)[mine])
+        else:
+            i_start, i_end = shard_bounds(NumSrc_total, rank, nprocs)   # list order: evolve.py:362-367
+            srcpos_flat, normflux_flat = format_sources(src_pos[:, i_start:i_end], src_flux[i_start:i_end])
     else:
         rank, nprocs = 0, 1
         srcpos_flat, normflux_flat = format_sources(src_pos, src_flux)
@@ -55,9 +68,14 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
     check(L.asora_buffer_upload(_cabi.BUF_XH, dptr(_flat(xh))))
     for b in (_cabi.BUF_XH_AV, _cabi.BUF_XH_INTERMED):  # xh_av = xh_intermed = copy(xh): evolve.py:136-137
         check(L.asora_buffer_copy(b, _cabi.BUF_XH))
-    phi_t = None
+    phi_t = xav_t = None
     if nprocs > 1:
+        import torch
         phi_t = device_tensor(L.asora_device_buffer(_cabi.BUF_PHI_ION), NumCells)
+        if halo is not None:
+            xav_t = device_tensor(L.asora_device_buffer(_cabi.BUF_XH_AV), NumCells)
+            check(L.asora_set_active_slab(*halo.active_range()))
+            scal = torch.zeros(3, dtype=torch.float64, device="cuda")
 
     if rank == 0:
         printlog("Calling evolve3D..." if nprocs == 1 else f"Calling evolve3D with {nprocs:n} ranks...", logfile, quiet)
@@ -82,17 +100,30 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
             check(L.asora_raytrace_device(float(R_max_LLS), float(sig), float(dr), 0, NumSrc, float(minlogtau),
                                           float(dlogtau), int(NumTau), 1))
             check(L.asora_sync())
-            if nprocs > 1:
-                import torch
+            if halo is not None:
+                halo.reduce_phi_(phi_t)       # neighbours' rates for my planes: 2 halos of h*N^2 doubles
+                torch.cuda.synchronize()
+            elif nprocs > 1:
                 allreduce_sum_(phi_t, group)  # evolve.py:433-437 (Reduce + Bcast) as one NCCL all-reduce
                 torch.cuda.synchronize()
             trt = time.time() - trt0
             tch0 = time.time()
-            check(L.asora_global_pass_device(float(dt), float(bh00), float(albpow), float(colh0), float(temph0),
-                                             float(abu_c), ctypes.byref(flag), ctypes.byref(s1), ctypes.byref(s0)))
+            if halo is not None:
+                o, cnt = halo.own_cells()
+                check(L.asora_global_pass_device_range(float(dt), float(bh00), float(albpow), float(colh0), float(temph0),
+                                                       float(abu_c), o, cnt, ctypes.byref(flag), ctypes.byref(s1),
+                                                       ctypes.byref(s0)))
+                scal.copy_(torch.tensor([flag.value, s1.value, s0.value], dtype=torch.float64))
+                allreduce_sum_(scal, group)   # conv_flag, sum x, sum 1-x over all planes
+                halo.gather_xh_(xav_t)        # my neighbours' new xh_av inside my ray-tracing reach
+                torch.cuda.synchronize()
+                g = scal.tolist()
+                conv_flag, sum_xh1_int, sum_xh0_int = int(round(g[0])), g[1], g[2]
+            else:
+                check(L.asora_global_pass_device(float(dt), float(bh00), float(albpow), float(colh0), float(temph0),
+                                                 float(abu_c), ctypes.byref(flag), ctypes.byref(s1), ctypes.byref(s0)))
+                conv_flag, sum_xh1_int, sum_xh0_int = flag.value, s1.value, s0.value
             tch = time.time() - tch0
-            conv_flag = flag.value
-            sum_xh1_int, sum_xh0_int = s1.value, s0.value
             # evolve.py:216-232
             rel_change_xh1 = abs((sum_xh1_int - prev_sum_xh1_int) / sum_xh1_int) if sum_xh1_int > 0.0 else 1.0
             rel_change_xh0 = abs((sum_xh0_int - prev_sum_xh0_int) / sum_xh0_int) if sum_xh0_int > 0.0 else 1.0
@@ -108,6 +139,13 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
                 raise RuntimeError("evolve3D: no convergence")
     finally:
         L.asora_set_sphere_only(0)
+        if halo is not None:
+            L.asora_set_active_slab(0, 0)
+    if halo is not None:
+        # once per time step: every rank gets the whole grids back (the reference API returns full arrays)
+        halo.assemble_(device_tensor(L.asora_device_buffer(_cabi.BUF_XH_INTERMED), NumCells))
+        halo.assemble_(phi_t)
+        torch.cuda.synchronize()
     if rank == 0:
         printlog("Multiple source convergence reached.", logfile, quiet)
     xh_new = np.empty(NumCells)
@@ -141,16 +179,21 @@ evolve3D.last_niter = 0
 
 def evolve3D_dist(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table, photo_thick_table, minlogtau,
                   dlogtau, R_max_LLS, convergence_fraction, sig, bh00, albpow, colh0, temph0, abu_c,
-                  logfile="pyC2Ray.log", quiet=False, group=None):
+                  logfile="pyC2Ray.log", quiet=False, group=None, decomposition="list"):
     """Source-sharded time step over the ranks of an initialised torch.distributed process group
     (backend nccl, one rank per GPU).  Every rank passes the full source list and gets the full
-    result."""
+    result.
+
+    decomposition: "list" -- contiguous blocks of the source list and one all-reduce of phi_ion per iteration
+    (the reference's scheme, evolve.py:360-373,433-437); "slab" -- sources sharded by position, halo exchanges
+    instead of N^3 collectives (parallel.SlabHalo); "auto" -- slab when the slabs are wide enough for the
+    ray-tracing radius, else list."""
     import torch.distributed as dist
     rank, nprocs = dist.get_rank(group), dist.get_world_size(group)
     shard = (rank, nprocs) if src_flux.shape[0] >= nprocs else None  # c2ray_base.py:185
     return _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table, minlogtau, dlogtau,
                           R_max_LLS, convergence_fraction, sig, bh00, albpow, colh0, temph0, abu_c, logfile,
-                          quiet or rank != 0, shard=shard, group=group)
+                          quiet or rank != 0, shard=shard, group=group, decomposition=decomposition)
 
 
 def evolve3D_MPI(dt, dr, src_flux, src_pos, use_gpu, max_subbox, subboxsize, loss_fraction, use_mpi, comm, rank,

@@ -33,6 +33,8 @@ SIGNATURES = {
     "asora_buffer_copy": (_i, [_i, _i]),
     "asora_raytrace_device": (_i, [_d, _d, _d, _i, _i, _d, _d, _i, _i]),
     "asora_global_pass_device": (_i, [_d, _d, _d, _d, _d, _d, ctypes.POINTER(_i), c_dp, c_dp]),
+    "asora_set_active_slab": (_i, [_i, _i]),
+    "asora_global_pass_device_range": (_i, [_d, _d, _d, _d, _d, _d, _i64, _i64, ctypes.POINTER(_i), c_dp, c_dp]),
     "asora_sync": (_i, []),
     "asora_set_stream": (_i, [ctypes.c_void_p]),
     "asora_debug_single_source": (_i, [_d, _d, _d, c_dp, _i, _d, _d, _i, c_dp, c_dp]),

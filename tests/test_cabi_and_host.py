@@ -176,3 +176,76 @@ def test_cosmology_bookkeeping():
     an = 2 / (3 * H0 * np.sqrt(0.73)) * np.arcsinh(np.sqrt(0.73 / 0.27) * 0.1 ** 1.5)
     assert 0.995 < t9 / an < 1.0
     assert abs(c.scale_factor(9.0) - 0.1) < 1e-15
+
+
+def test_slab_edges():
+    from pyc2ray_b200.parallel import slab_edges
+    rng = np.random.RandomState(0)
+    x = rng.randint(0, 256, size=10000)
+    edges, h = slab_edges(x, 256, 8, 10.76)
+    assert h == 11 and edges[0] == 0 and edges[-1] == 256 and len(edges) == 9
+    counts = [np.sum((x >= edges[r]) & (x < edges[r + 1])) for r in range(8)]
+    assert sum(counts) == 10000 and max(counts) - min(counts) < 300
+    assert all(edges[r + 1] - edges[r] >= 2 * h for r in range(8))
+    assert slab_edges(x, 256, 8, 30.0)[0] is None            # 8 slabs of 32 planes cannot hold two 31-plane halos
+    assert slab_edges(x, 256, 1, 5.0)[0] is None
+    clustered = np.full(1000, 17)
+    e2, h2 = slab_edges(clustered, 128, 2, 4.5)               # all sources in one plane: widths are enforced
+    assert e2 is not None and all(e2[r + 1] - e2[r] >= 2 * h2 for r in range(2))
+
+
+def _slab_rank_main(rank, world, port, outdir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import oracle
+    from pyc2ray_b200.parallel import slab_edges, SlabHalo
+    from pyc2ray_b200.utils.sourceutils import format_sources
+    from tests.fields import make_case
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    c = make_case("multi_n32")
+    N, R = c["N"], 3.3
+    x0 = c["srcpos"][0] - 1
+    edges, h = slab_edges(x0, N, world, R)
+    halo = SlabHalo(edges, h, N, rank, world)
+    mine = (x0 >= edges[rank]) & (x0 < edges[rank + 1])
+    pos_flat, flux_flat = format_sources(c["srcpos"][:, mine], c["flux"][mine])
+    phi, _, _ = oracle.asora_do_all_sources(R, c["sig"], c["dr"], c["ndens"].ravel(), c["xh"].ravel(), pos_flat, flux_flat, N,
+                                            c["thin"], c["thick"], c["minlogtau"], c["dlogtau"], c["NumTau"])
+    t = torch.from_numpy(phi)
+    halo.reduce_phi_(t)
+    # xh halo gather: every rank marks its own planes with its rank id
+    xh = torch.full((N ** 3,), -1.0, dtype=torch.float64)
+    o, cnt = halo.own_cells()
+    xh[o:o + cnt] = float(rank)
+    halo.gather_xh_(xh)
+    np.save(os.path.join(outdir, f"xh_{rank}.npy"), xh.numpy().copy())
+    halo.assemble_(t)
+    np.save(os.path.join(outdir, f"phi_{rank}.npy"), t.numpy())
+    np.save(os.path.join(outdir, f"edges_{rank}.npy"), np.array(edges + [h]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_decomposition_over_gloo(tmp_path, world):
+    """Slab-sharded sources + halo reduction of the rates + assembly == single-process result; the xh_av halo gather
+    delivers the neighbours' planes.  CPU ranks over gloo, the oracle standing in for the GPU sweep."""
+    import torch.multiprocessing as mp
+    import oracle
+    from tests.fields import make_case
+    port = _free_port()
+    mp.spawn(_slab_rank_main, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    c = make_case("multi_n32")
+    N = c["N"]
+    ref, _, _ = oracle.asora_do_all_sources(3.3, c["sig"], c["dr"], c["ndens"].ravel(), c["xh"].ravel(), c["pos_flat"],
+                                            c["flux_flat"], N, c["thin"], c["thick"], c["minlogtau"], c["dlogtau"], c["NumTau"])
+    e = np.load(tmp_path / "edges_0.npy")
+    edges, h = list(e[:-1]), int(e[-1])
+    for r in range(world):
+        np.testing.assert_allclose(np.load(tmp_path / f"phi_{r}.npy"), ref, rtol=1e-12, atol=0)
+        xh = np.load(tmp_path / f"xh_{r}.npy").reshape(N, N, N)
+        assert (xh[edges[r]:edges[r + 1]] == r).all()
+        assert (xh[[(edges[r] - k) % N for k in range(1, h + 1)]] == (r - 1) % world).all()
+        assert (xh[[(edges[r + 1] + k) % N for k in range(h)]] == (r + 1) % world).all()

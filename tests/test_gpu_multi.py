@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, outdir):
+def _worker(rank, world, port, outdir, decomposition="list", R=None):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), ASORA_QUIET="1")
     import torch
@@ -29,12 +29,13 @@ def _worker(rank, world, port, outdir):
     p.device_init(N, 8)
     p.photo_table_to_device(c["thin"], c["thick"])
     x, phi = p.evolve3D_dist(1e6 * 3.15576e7, c["dr"], flux, c["srcpos"], temp, c["ndens"], xh0, c["thin"], c["thick"],
-                             c["minlogtau"], c["dlogtau"], c["R"], 1e-4, c["sig"], *chem, logfile=None, quiet=True)
+                             c["minlogtau"], c["dlogtau"], R or c["R"], 1e-4, c["sig"], *chem, logfile=None, quiet=True,
+                             decomposition=decomposition)
     np.save(os.path.join(outdir, f"x_{rank}.npy"), x)
     np.save(os.path.join(outdir, f"phi_{rank}.npy"), phi)
     if rank == 0:
         x1, phi1 = p.evolve3D(1e6 * 3.15576e7, c["dr"], flux, c["srcpos"], True, 0, 0, 0, temp, c["ndens"], xh0, c["thin"],
-                              c["thick"], c["minlogtau"], c["dlogtau"], c["R"], 1e-4, c["sig"], *chem, logfile=None, quiet=True)
+                              c["thick"], c["minlogtau"], c["dlogtau"], R or c["R"], 1e-4, c["sig"], *chem, logfile=None, quiet=True)
         np.save(os.path.join(outdir, "x_single.npy"), x1)
         np.save(os.path.join(outdir, "phi_single.npy"), phi1)
     p.device_close()
@@ -56,5 +57,26 @@ def test_two_gpu_evolve_matches_single_gpu(tmp_path):
     p0, p1, ps = (np.load(tmp_path / f) for f in ("phi_0.npy", "phi_1.npy", "phi_single.npy"))
     np.testing.assert_array_equal(x0, x1)      # identical all-reduced phi -> identical deterministic chemistry
     np.testing.assert_array_equal(p0, p1)
+    np.testing.assert_allclose(x0, xs, rtol=1e-10, atol=1e-16)
+    np.testing.assert_allclose(p0, ps, rtol=1e-10, atol=1e-12 * ps.max())
+
+
+def test_two_gpu_slab_decomposition_matches_single_gpu(tmp_path):
+    """Position-sharded sources with halo exchanges (no N^3 collective inside the convergence loop) must reproduce
+    the single-GPU time step."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(2, port, str(tmp_path), "slab", 3.3), nprocs=2, join=True)
+    x0, x1, xs = (np.load(tmp_path / f) for f in ("x_0.npy", "x_1.npy", "x_single.npy"))
+    p0, p1, ps = (np.load(tmp_path / f) for f in ("phi_0.npy", "phi_1.npy", "phi_single.npy"))
+    np.testing.assert_array_equal(x0, x1)
+    np.testing.assert_array_equal(p0, p1)
+    assert xs.mean() > 3e-4
     np.testing.assert_allclose(x0, xs, rtol=1e-10, atol=1e-16)
     np.testing.assert_allclose(p0, ps, rtol=1e-10, atol=1e-12 * ps.max())
