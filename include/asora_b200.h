@@ -96,6 +96,10 @@ void* asora_device_buffer(int which);
 int asora_buffer_upload(int which, const double* host);
 int asora_buffer_download(int which, double* host);
 
+/* Host -> device copy of cells [cell_offset, cell_offset + cell_count) of a named buffer; `host` points at the
+ * first cell of the WHOLE host grid (the same offset is applied on both sides). */
+int asora_buffer_upload_range(int which, const double* host, int64_t cell_offset, int64_t cell_count);
+
 /* Device -> device copy between two named buffers (N^3 doubles), on the context's stream. */
 int asora_buffer_copy(int dst, int src);
 

@@ -534,6 +534,19 @@ int asora_buffer_upload(int which, const double* host)
     return 0;
 }
 
+int asora_buffer_upload_range(int which, const double* host, int64_t cell_offset, int64_t cell_count)
+{
+    if (int rc = need_init()) return rc;
+    if (int rc = ensure_buffer(which)) return rc;
+    if (!host || cell_offset < 0 || cell_count < 0 || cell_offset + cell_count > g.ncell)
+        return fail("buffer_upload_range: bad range");
+    if (cell_count > 0)
+        CK(cudaMemcpyAsync(g.buf[which] + cell_offset, host + cell_offset, sizeof(double) * cell_count,
+                           cudaMemcpyHostToDevice, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
 int asora_buffer_download(int which, double* host)
 {
     if (int rc = need_init()) return rc;

@@ -63,9 +63,18 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
     NumSrc = normflux_flat.shape[0]
 
     check(L.asora_source_data_to_device(iptr(srcpos_flat), dptr(normflux_flat), NumSrc))
-    check(L.asora_buffer_upload(_cabi.BUF_NDENS, dptr(_flat(ndens))))
-    check(L.asora_buffer_upload(_cabi.BUF_TEMP, dptr(_flat(temp))))
-    check(L.asora_buffer_upload(_cabi.BUF_XH, dptr(_flat(xh))))
+    if halo is None:
+        check(L.asora_buffer_upload(_cabi.BUF_NDENS, dptr(_flat(ndens))))
+        check(L.asora_buffer_upload(_cabi.BUF_TEMP, dptr(_flat(temp))))
+        check(L.asora_buffer_upload(_cabi.BUF_XH, dptr(_flat(xh))))
+    else:
+        # a rank only ever reads its own planes and the halos: upload just those (at most two segments)
+        first, count = halo.active_range()
+        segs = [(first, min(count, N - first)), (0, count - min(count, N - first))]
+        for buf, arr in ((_cabi.BUF_NDENS, _flat(ndens)), (_cabi.BUF_TEMP, _flat(temp)), (_cabi.BUF_XH, _flat(xh))):
+            for b, c in segs:
+                if c > 0:
+                    check(L.asora_buffer_upload_range(buf, dptr(arr), b * N * N, c * N * N))
     for b in (_cabi.BUF_XH_AV, _cabi.BUF_XH_INTERMED):  # xh_av = xh_intermed = copy(xh): evolve.py:136-137
         check(L.asora_buffer_copy(b, _cabi.BUF_XH))
     phi_t = xav_t = None
@@ -128,7 +137,7 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
             rel_change_xh1 = abs((sum_xh1_int - prev_sum_xh1_int) / sum_xh1_int) if sum_xh1_int > 0.0 else 1.0
             rel_change_xh0 = abs((sum_xh0_int - prev_sum_xh0_int) / sum_xh0_int) if sum_xh0_int > 0.0 else 1.0
             if rank == 0:
-                printlog(f"Raytracing took {trt:.3f} s, chemistry {tch:.3f} s. Number of non-converged points: "
+                printlog(f"Raytracing took {trt*1e3:.2f} ms, chemistry {tch*1e3:.2f} ms. Number of non-converged points: "
                          f"{conv_flag} of {NumCells} ({conv_flag / NumCells * 100 : .3f} % ), Relative change in "
                          f"ionfrac: {rel_change_xh1 : .2e}", logfile, quiet)
             converged = (conv_flag < conv_criterion) or ((rel_change_xh1 < convergence_fraction) and
@@ -179,7 +188,7 @@ evolve3D.last_niter = 0
 
 def evolve3D_dist(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table, photo_thick_table, minlogtau,
                   dlogtau, R_max_LLS, convergence_fraction, sig, bh00, albpow, colh0, temph0, abu_c,
-                  logfile="pyC2Ray.log", quiet=False, group=None, decomposition="list"):
+                  logfile="pyC2Ray.log", quiet=False, group=None, decomposition="auto"):
     """Source-sharded time step over the ranks of an initialised torch.distributed process group
     (backend nccl, one rank per GPU).  Every rank passes the full source list and gets the full
     result.
