@@ -42,6 +42,10 @@ struct Context {
     double* src_flux_sorted = nullptr;  // then sweep neighbouring regions and share ndens/phi lines in L2
     int nsrc = 0;
     SweepPlan plan;
+    // temperature factors of the chemistry (chemistry.cu), valid for the TEMP buffer contents and constants below
+    double2* chem_factors = nullptr;
+    bool chem_factors_valid = false;
+    double cf_bh00 = 0, cf_albpow = 0, cf_colh0 = 0, cf_temph0 = 0;
     // chemistry scratch
     double* chem_partials = nullptr;
     int* chem_iparts = nullptr;
@@ -110,6 +114,24 @@ int ensure_chem_scratch()
         CK(cudaMalloc(&g.chem_partials, sizeof(double) * (2 * g.chem_blocks + 2)));
         CK(cudaMalloc(&g.chem_iparts, sizeof(int) * (g.chem_blocks + 1)));
     }
+    return 0;
+}
+
+// Temperature factors for the device-resident chemistry: refilled when the TEMP buffer was rewritten or the
+// constants changed (whole grid, also in slab-decomposed runs: stale planes are never read).
+int ensure_chem_factors(double bh00, double albpow, double colh0, double temph0)
+{
+    if (!g.chem_factors) CK(cudaMalloc(&g.chem_factors, sizeof(double2) * g.ncell));
+    if (g.chem_factors_valid && g.cf_bh00 == bh00 && g.cf_albpow == albpow && g.cf_colh0 == colh0 && g.cf_temph0 == temph0)
+        return 0;
+    cudaError_t e = launch_temperature_factors(g.buf[ASORA_BUF_TEMP], g.chem_factors, bh00, albpow, colh0, temph0, g.ncell,
+                                               g.stream);
+    if (e != cudaSuccess) return fail_cuda("temperature_factors_kernel launch", e);
+    g.chem_factors_valid = true;
+    g.cf_bh00 = bh00;
+    g.cf_albpow = albpow;
+    g.cf_colh0 = colh0;
+    g.cf_temph0 = temph0;
     return 0;
 }
 
@@ -358,6 +380,9 @@ int asora_device_close(void)
     if (g.src_flux_sorted) cudaFree(g.src_flux_sorted);
     g.src_pos_sorted = nullptr;
     g.src_flux_sorted = nullptr;
+    if (g.chem_factors) cudaFree(g.chem_factors);
+    g.chem_factors = nullptr;
+    g.chem_factors_valid = false;
     if (g.chem_partials) cudaFree(g.chem_partials);
     if (g.chem_iparts) cudaFree(g.chem_iparts);
     for (int i = 0; i < 6; i++) {
@@ -521,6 +546,7 @@ void* asora_device_buffer(int which)
 {
     if (need_init()) return nullptr;
     if (ensure_buffer(which)) return nullptr;
+    if (which == ASORA_BUF_TEMP) g.chem_factors_valid = false;  // the caller may write through the pointer
     cudaStreamSynchronize(g.stream);
     return g.buf[which];
 }
@@ -529,6 +555,7 @@ int asora_buffer_upload(int which, const double* host)
 {
     if (int rc = need_init()) return rc;
     if (int rc = ensure_buffer(which)) return rc;
+    if (which == ASORA_BUF_TEMP) g.chem_factors_valid = false;
     CK(cudaMemcpyAsync(g.buf[which], host, sizeof(double) * g.ncell, cudaMemcpyHostToDevice, g.stream));
     CK(cudaStreamSynchronize(g.stream));
     return 0;
@@ -540,6 +567,7 @@ int asora_buffer_upload_range(int which, const double* host, int64_t cell_offset
     if (int rc = ensure_buffer(which)) return rc;
     if (!host || cell_offset < 0 || cell_count < 0 || cell_offset + cell_count > g.ncell)
         return fail("buffer_upload_range: bad range");
+    if (which == ASORA_BUF_TEMP) g.chem_factors_valid = false;
     if (cell_count > 0)
         CK(cudaMemcpyAsync(g.buf[which] + cell_offset, host + cell_offset, sizeof(double) * cell_count,
                            cudaMemcpyHostToDevice, g.stream));
@@ -584,7 +612,9 @@ int asora_global_pass_device_range(double dt, double bh00, double albpow, double
         return 0;
     }
     const int64_t o = cell_offset;
-    cudaError_t e = launch_global_pass(dt, g.buf[ASORA_BUF_NDENS] + o, g.buf[ASORA_BUF_TEMP] + o, g.buf[ASORA_BUF_XH] + o,
+    if (int rc = ensure_chem_factors(bh00, albpow, colh0, temph0)) return rc;
+    cudaError_t e = launch_global_pass(dt, g.buf[ASORA_BUF_NDENS] + o, g.buf[ASORA_BUF_TEMP] + o, g.chem_factors + o,
+                                       g.buf[ASORA_BUF_XH] + o,
                                        g.buf[ASORA_BUF_XH_AV] + o, g.buf[ASORA_BUF_XH_INTERMED] + o,
                                        g.buf[ASORA_BUF_PHI_ION] + o, bh00, albpow, colh0, temph0, abu_c, cell_count, 1,
                                        g.chem_partials, g.chem_iparts, g.chem_blocks, conv_flag, sum_xh1, sum_xh0, g.stream);
@@ -597,6 +627,7 @@ int asora_buffer_copy(int dst, int src)
     if (int rc = need_init()) return rc;
     if (int rc = ensure_buffer(dst)) return rc;
     if (int rc = ensure_buffer(src)) return rc;
+    if (dst == ASORA_BUF_TEMP) g.chem_factors_valid = false;
     if (dst != src)
         CK(cudaMemcpyAsync(g.buf[dst], g.buf[src], sizeof(double) * g.ncell, cudaMemcpyDeviceToDevice, g.stream));
     return 0;
@@ -611,7 +642,8 @@ int asora_global_pass_device(double dt, double bh00, double albpow, double colh0
     for (int id : ids)
         if (int rc = ensure_buffer(id)) return rc;
     if (int rc = ensure_chem_scratch()) return rc;
-    cudaError_t e = launch_global_pass(dt, g.buf[ASORA_BUF_NDENS], g.buf[ASORA_BUF_TEMP], g.buf[ASORA_BUF_XH],
+    if (int rc = ensure_chem_factors(bh00, albpow, colh0, temph0)) return rc;
+    cudaError_t e = launch_global_pass(dt, g.buf[ASORA_BUF_NDENS], g.buf[ASORA_BUF_TEMP], g.chem_factors, g.buf[ASORA_BUF_XH],
                                        g.buf[ASORA_BUF_XH_AV], g.buf[ASORA_BUF_XH_INTERMED], g.buf[ASORA_BUF_PHI_ION],
                                        bh00, albpow, colh0, temph0, abu_c, g.ncell, 1, g.chem_partials,
                                        g.chem_iparts, g.chem_blocks, conv_flag, sum_xh1, sum_xh0, g.stream);
@@ -649,7 +681,7 @@ int asora_global_pass(double dt, const double* ndens, const double* temp, const 
         if (dev[i] == g.chem_stage[i]) CK(cudaMemcpyAsync(dev[i], src[i], bytes, cudaMemcpyHostToDevice, st));
     }
     int flag = 0;
-    cudaError_t e = launch_global_pass(dt, dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], bh00, albpow, colh0,
+    cudaError_t e = launch_global_pass(dt, dev[0], dev[1], nullptr, dev[2], dev[3], dev[4], dev[5], bh00, albpow, colh0,
                                        temph0, abu_c, ncell, 1, g.chem_partials, g.chem_iparts, g.chem_blocks,
                                        &flag, nullptr, nullptr, st);
     if (e != cudaSuccess) return fail_cuda("global_pass_kernel", e);

@@ -133,8 +133,10 @@ cudaError_t launch_pair_table(const double* table, double2* pairs, int ntab, cud
 void host_log2_table(double* tab512);
 
 // chemistry.cu
-cudaError_t launch_global_pass(double dt, const double* ndens, const double* temp, const double* xh,
-                               double* xh_av, double* xh_intermed, const double* phi_ion, double bh00,
+cudaError_t launch_temperature_factors(const double* temp, double2* factors, double bh00, double albpow, double colh0,
+                                       double temph0, int64_t ncell, cudaStream_t stream);
+cudaError_t launch_global_pass(double dt, const double* ndens, const double* temp, const double2* factors,
+                               const double* xh, double* xh_av, double* xh_intermed, const double* phi_ion, double bh00,
                                double albpow, double colh0, double temph0, double abu_c, int64_t ncell,
                                int store_av_first, double* d_partials, int* d_iparts, int nblocks_max,
                                int* conv_flag, double* sum1, double* sum0, cudaStream_t stream);

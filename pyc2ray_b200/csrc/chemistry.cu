@@ -14,8 +14,29 @@
 #define CHEM_MIN_FRAC_CHANGE ((double)1.0e-3f)
 #define CHEM_MIN_FRAC_ATOMS ((double)1.0e-8f)
 
+// The two temperature-only factors of doric (chemistry.f90:257-262): recombination and collisional ionisation
+// coefficients.  They cost a pow, a sqrt and an exp per cell, more than the rest of a converged cell's update, and the
+// run is isothermal: the convergence loop of one time step calls global_pass ~30 times with the same temperatures.
+// PRE = true reads them from a grid filled once per (temperature grid, constants) by temperature_factors_kernel.
+__device__ __forceinline__ double2 temperature_factors(double temp_p, double bh00, double albpow, double colh0, double temph0)
+{
+    const double brech0 = 1.0 * bh00 * pow(temp_p / 1e4, albpow);                 // clumping = 1 (chemistry.f90:168)
+    const double acolh0 = colh0 * sqrt(temp_p) * exp(-temph0 / temp_p);
+    return make_double2(brech0, acolh0);
+}
+
+__global__ void __launch_bounds__(CHEM_BLOCK)
+temperature_factors_kernel(const double* __restrict__ temp, double2* __restrict__ factors, double bh00, double albpow,
+                           double colh0, double temph0, int64_t ncell)
+{
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < ncell; p += (int64_t)gridDim.x * blockDim.x)
+        factors[p] = temperature_factors(temp[p], bh00, albpow, colh0, temph0);
+}
+
+template <bool PRE>
 __global__ void __launch_bounds__(CHEM_BLOCK)
 global_pass_kernel(double dt, const double* __restrict__ ndens, const double* __restrict__ temp,
+                   const double2* __restrict__ factors,
                    const double* xh, double* xh_av, double* xh_intermed, const double* __restrict__ phi_ion,
                    double bh00, double albpow, double colh0, double temph0, double abu_c, int64_t ncell,
                    int store_av_first, double* __restrict__ partials, int* __restrict__ iparts)
@@ -25,7 +46,6 @@ global_pass_kernel(double dt, const double* __restrict__ ndens, const double* __
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < ncell;
          p += (int64_t)gridDim.x * blockDim.x) {
         // chemistry.f90:81-91
-        const double temp_p = temp[p];
         const double ndens_p = ndens[p];
         const double phi_p = phi_ion[p];
         const double xh_p = xh[p];
@@ -35,8 +55,8 @@ global_pass_kernel(double dt, const double* __restrict__ ndens, const double* __
         double xh_int_p = 0.0;
 
         // doric, temperature-only factors (chemistry.f90:257-262); isothermal, so loop-invariant
-        const double brech0 = 1.0 * bh00 * pow(temp_p / 1e4, albpow);
-        const double acolh0 = colh0 * sqrt(temp_p) * exp(-temph0 / temp_p);
+        const double2 tf = PRE ? factors[p] : temperature_factors(temp[p], bh00, albpow, colh0, temph0);
+        const double brech0 = tf.x, acolh0 = tf.y;
 
         // do_chemistry fixed point on the time-averaged electron density (chemistry.f90:143-203)
         int nit = 0;
@@ -147,17 +167,31 @@ int chemistry_partial_blocks(int64_t ncell)
 }
 
 // partials: 2*nblocks doubles followed by 2 result doubles; iparts: nblocks ints followed by 1 result.
-cudaError_t launch_global_pass(double dt, const double* ndens, const double* temp, const double* xh,
-                               double* xh_av, double* xh_intermed, const double* phi_ion, double bh00,
+cudaError_t launch_temperature_factors(const double* temp, double2* factors, double bh00, double albpow, double colh0,
+                                       double temph0, int64_t ncell, cudaStream_t stream)
+{
+    temperature_factors_kernel<<<chemistry_partial_blocks(ncell), CHEM_BLOCK, 0, stream>>>(temp, factors, bh00, albpow,
+                                                                                        colh0, temph0, ncell);
+    return cudaGetLastError();
+}
+
+// `factors` may be null: the temperature factors are then evaluated per cell inside the pass.
+cudaError_t launch_global_pass(double dt, const double* ndens, const double* temp, const double2* factors,
+                               const double* xh, double* xh_av, double* xh_intermed, const double* phi_ion, double bh00,
                                double albpow, double colh0, double temph0, double abu_c, int64_t ncell,
                                int store_av_first, double* d_partials, int* d_iparts, int nblocks_max,
                                int* conv_flag, double* sum1, double* sum0, cudaStream_t stream)
 {
     int nb = chemistry_partial_blocks(ncell);
     if (nb > nblocks_max) nb = nblocks_max;
-    global_pass_kernel<<<nb, CHEM_BLOCK, 0, stream>>>(dt, ndens, temp, xh, xh_av, xh_intermed, phi_ion, bh00,
-                                                      albpow, colh0, temph0, abu_c, ncell, store_av_first,
-                                                      d_partials, d_iparts);
+    if (factors)
+        global_pass_kernel<true><<<nb, CHEM_BLOCK, 0, stream>>>(dt, ndens, temp, factors, xh, xh_av, xh_intermed, phi_ion,
+                                                                bh00, albpow, colh0, temph0, abu_c, ncell, store_av_first,
+                                                                d_partials, d_iparts);
+    else
+        global_pass_kernel<false><<<nb, CHEM_BLOCK, 0, stream>>>(dt, ndens, temp, factors, xh, xh_av, xh_intermed, phi_ion,
+                                                                 bh00, albpow, colh0, temph0, abu_c, ncell, store_av_first,
+                                                                 d_partials, d_iparts);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     global_pass_finish_kernel<<<1, CHEM_BLOCK, 0, stream>>>(d_partials, d_iparts, nb, d_partials + 2 * nblocks_max,
