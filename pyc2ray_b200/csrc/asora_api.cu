@@ -162,7 +162,8 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     p.R2 = R * R;
     p.sig = sig;
     p.dr = dr;
-    p.inv_volfac = 1.0 / (ASORA_FOURPI * (dr * dr * dr));
+    p.kpref = (sig * dr) / (ASORA_FOURPI * (dr * dr * dr));
+    p.tau_max = sig * ASORA_MAX_COLDENSH;
     // rates.cu:77-78: index = 1 + (log10(tau) - minlogtau)/dlogtau = lut_a + lut_b * log2(tau)
     p.lut_b = 0.30102999566398119521 / dlogtau;
     p.lut_a = 1.0 - minlogtau / dlogtau;
@@ -288,7 +289,7 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
         for (int sg = 0; sg < 2; sg++) {
             if (seg_len[sg] <= 0) continue;
             cudaError_t e = launch_prepare_nhi(g.buf[ASORA_BUF_NDENS] + seg_off[sg], g.buf[ASORA_BUF_XH_AV] + seg_off[sg],
-                                               g.nhi + seg_off[sg], seg_len[sg], g.stream);
+                                               g.nhi + seg_off[sg], sig * dr, seg_len[sg], g.stream);
             if (e != cudaSuccess) return fail_cuda("prepare_nhi_kernel launch", e);
             g.last_launches += 1;
             if (zero_phi)
@@ -303,6 +304,11 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     } else {
         cudaError_t e = launch_sweep_grid(p, groups, g.grid_counters, g.stream, &g.last_launches, &g.last_levels);
         if (e != cudaSuccess) return fail_cuda("sweep_grid_kernel launch", e);
+    }
+    if (coldens_grid) {
+        // the kernels store optical depths; the debug interface promises column densities
+        cudaError_t e = launch_scale_grid(coldens_grid, 1.0 / sig, g.ncell, g.stream);
+        if (e != cudaSuccess) return fail_cuda("scale_grid_kernel launch", e);
     }
     CK(cudaEventRecord(g.ev1, g.stream));
     g.last_variant = variant;

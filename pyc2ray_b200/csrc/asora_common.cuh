@@ -70,13 +70,14 @@ struct SweepParams {
     int last_l, last_r;       // raytracing.cu:122-123
     double R2;                // R*R
     double sig, dr;
-    double inv_volfac;        // 1 / (4 pi dr^3)
+    double kpref;             // sigma * dr / (4 pi dr^3): rate prefactor in optical-depth units (sweep_kernels.cu)
+    double tau_max;           // sigma * MAX_COLDENSH: no rate beyond this incoming optical depth (raytracing.cu:315)
     double lut_a, lut_b;      // table index = lut_a + lut_b * log2(tau)  (rates.cu:77-78)
     double tau_lo, tau_hi;    // optical depths at which that index reaches 0 (>= 1e-20) and NumTau
     double minlogtau, dlogtau;
     int NumTau;               // index clamp as passed by the caller (rates.cu:78-79)
     int ntab;                 // uploaded table length
-    const double* nhi;        // ndens * (1 - xh_av), refreshed before every sweep (raytracing.cu:275-276)
+    const double* nhi;        // ntau = ndens * (1 - xh_av) * sigma * dr, refreshed before every sweep
     double* phi_ion;
     const double2* thin;      // {T[i], T[i+1]-T[i]} pairs of the uploaded tables
     const double2* thick;
@@ -85,7 +86,7 @@ struct SweepParams {
     const double* src_flux;
     int src_begin, src_count;
     int sphere_only;          // grid-cooperative variant: skip cells outside the R sphere
-    double* coldens_out;      // optional N^3 grid receiving outgoing column densities (debug) or
+    double* coldens_out;      // optional N^3 grid receiving outgoing optical depths (debug) or
                               // the L2-resident scratch of the grid-cooperative variant
 };
 
@@ -128,7 +129,9 @@ int sweep_grid_groups(const SweepParams& p, int max_groups, int* total_ctas_out,
 cudaError_t launch_sweep_grid(const SweepParams& p, int ngroups, unsigned* counters, cudaStream_t stream,
                               int* launches, int* levels);
 
-cudaError_t launch_prepare_nhi(const double* ndens, const double* xh_av, double* nhi, int64_t ncell, cudaStream_t stream);
+cudaError_t launch_prepare_nhi(const double* ndens, const double* xh_av, double* ntau, double sig_dr, int64_t ncell,
+                               cudaStream_t stream);
+cudaError_t launch_scale_grid(double* grid, double factor, int64_t ncell, cudaStream_t stream);
 cudaError_t launch_pair_table(const double* table, double2* pairs, int ntab, cudaStream_t stream);
 void host_log2_table(double* tab512);
 

@@ -110,9 +110,11 @@ __device__ __forceinline__ double photo_lookup(const double2* __restrict__ pairs
 // Corners whose bilinear weight is exactly zero never contribute (the reference multiplies whatever it
 // reads by 0: raytracing.cu:416-428, SURVEY note N3).  MASK: the caller may have read stale memory
 // for those corners, so force them to 0; the plan-driven sweep instead points them at a live slot.
+// The kernels work in optical-depth units: every stored column is tau = sigma * N_HI (the pre-pass folds sigma and
+// dr into the per-cell opacity), so c_i * sigma of the reference is the stored value itself.
 template <bool MASK>
 __device__ __forceinline__ double interp_coldens(double c1, double c2, double c3, double c4, double wA,
-                                                 double wB, double sig, unsigned flags)
+                                                 double wB, unsigned flags)
 {
     const double uA = 1.0 - wA, uB = 1.0 - wB;
     const double s1 = wA * wB, s2 = wB * uA, s3 = wA * uB, s4 = uA * uB;
@@ -122,8 +124,8 @@ __device__ __forceinline__ double interp_coldens(double c1, double c2, double c3
         c3 = (s3 != 0.0) ? c3 : 0.0;
         c4 = (s4 != 0.0) ? c4 : 0.0;
     }
-    const double m1 = dmax(c1 * sig, 0.6), m2 = dmax(c2 * sig, 0.6);
-    const double m3 = dmax(c3 * sig, 0.6), m4 = dmax(c4 * sig, 0.6);
+    const double m1 = dmax(c1, 0.6), m2 = dmax(c2, 0.6);
+    const double m3 = dmax(c3, 0.6), m4 = dmax(c4, 0.6);
     const double m12 = m1 * m2, m34 = m3 * m4;
     double w1 = s1 * (m2 * m34), w2 = s2 * (m1 * m34);
     double w3 = s3 * (m4 * m12), w4 = s4 * (m3 * m12);
@@ -131,7 +133,7 @@ __device__ __forceinline__ double interp_coldens(double c1, double c2, double c3
     double cdensi;
     if (den < 1e300) {
         cdensi = fast_div(fma(c1, w1, c2 * w2) + fma(c3, w3, c4 * w4), den);
-    } else {  // the products overflowed (column densities beyond 1e90): the reference's literal form
+    } else {  // the products overflowed (optical depths beyond 1e90): the reference's literal form
         w1 = s1 / m1, w2 = s2 / m2, w3 = s3 / m3, w4 = s4 / m4;
         cdensi = (c1 * w1 + c2 * w2 + c3 * w3 + c4 * w4) / (w1 + w2 + w3 + w4);
     }
@@ -147,29 +149,32 @@ __device__ __forceinline__ int wrap(int i, int N)
     return i;
 }
 
-// Everything after the incoming column density is known: raytracing.cu:300-329 + rates.cu:16-41.
-// Returns the outgoing column density.
-__device__ __forceinline__ double finish_cell(double coldensh_in, double path_cells, double inv_np, unsigned flags,
-                                              double nHI_p, double strength, size_t pos, const SweepParams& p,
+// Everything after the incoming optical depth is known: raytracing.cu:300-329 + rates.cu:16-41, with
+//   ntau     = nHI * sigma * dr            opacity of the cell per unit path in cell units (pre-pass)
+//   tau_out  = tau_in + ntau * path        sigma * (coldensh_in + nHI * path * dr)          (raytracing.cu:311)
+//   phi      = strength / Vfact * absorbed / nHI = strength * inv_np * kpref * absorbed / ntau,
+//              kpref = sigma * dr / (4 pi dr^3)                                   (rates.cu:24, raytracing.cu:324)
+// Returns the outgoing optical depth.
+__device__ __forceinline__ double finish_cell(double tau_in, double path_cells, double inv_np, unsigned flags,
+                                              double ntau_p, double strength, size_t pos, const SweepParams& p,
                                               const double2* __restrict__ log2_tab)
 {
-    const double cdho = fma(nHI_p, path_cells * p.dr, coldensh_in);
-    if ((flags & PC_RATED) && coldensh_in <= ASORA_MAX_COLDENSH) {
-        const double tau_in = coldensh_in * p.sig;
-        const double tau_out = cdho * p.sig;
+    const double tau_out = fma(ntau_p, path_cells, tau_in);
+    if ((flags & PC_RATED) && tau_in <= p.tau_max) {  // coldensh_in <= MAX_COLDENSH (raytracing.cu:315)
         const double dtau = tau_out - tau_in;
         const bool thick = fabs(dtau) > ASORA_TAU_PHOTO_LIMIT;
         const double t_in = photo_lookup(p.thick, tau_in, p, log2_tab);
         const double t_out = photo_lookup(thick ? p.thick : p.thin, tau_out, p, log2_tab);
         // rates.cu:28-38: thick cells absorb T(tau_in) - T(tau_out), thin cells dtau * T_thin(tau_out)
         const double absorbed = thick ? (t_in - t_out) : dtau * t_out;
-        const double num = (strength * (inv_np * p.inv_volfac)) * absorbed;  // prefact * ...  (rates.cu:24)
-        // raytracing.cu:324.  nHI == 0 (fully ionised input cell) divides by zero in the reference too.
-        const double phi = (nHI_p != 0.0) ? fast_div(num, nHI_p) : num / nHI_p;
+        const double num = (strength * (inv_np * p.kpref)) * absorbed;
+        // nHI == 0 (fully ionised input cell) divides by zero in the reference too (raytracing.cu:324); the
+        // reciprocal-based division is only used where its flush-to-zero seed is safe
+        const double phi = (ntau_p > 1e-290 && ntau_p < 1e290) ? fast_div(num, ntau_p) : num / ntau_p;
         // one fire-and-forget fp64 reduction per rated (source, cell) pair: RED.E.ADD.F64 at L2
         atomicAdd(p.phi_ion + pos, phi);
     }
-    return cdho;
+    return tau_out;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -274,7 +279,7 @@ sweep_smem_kernel(const int4* __restrict__ plan, int ncells, const int* __restri
             for (int s = 0; s < S; s++) {
                 if (!live[s]) continue;
                 const double* pv = prev + s * max_level_cells;
-                const double cin = interp_coldens<false>(pv[c.nb1], pv[c.nb2], pv[c.nb3], pv[c.nb4], c.wA, c.wB, p.sig, c.flags);
+                const double cin = interp_coldens<false>(pv[c.nb1], pv[c.nb2], pv[c.nb3], pv[c.nb4], c.wA, c.wB, c.flags);
                 const double cdho = finish_cell(cin, c.path, c.inv_np, c.flags, c.nhi[s], flux[s], c.pos[s], p, log2_tab);
                 cur[s * max_level_cells + slot] = cdho;
                 if (p.coldens_out) p.coldens_out[c.pos[s]] = cdho;
@@ -457,7 +462,7 @@ sweep_grid_kernel(SweepParams p, int nlevels, int ngroups, int group_ctas, unsig
                     const double c2 = (wB * (1.0 - wA) != 0.0) ? __ldcg(slab + q2) : 0.0;
                     const double c3 = (wA * (1.0 - wB) != 0.0) ? __ldcg(slab + q3) : 0.0;
                     const double c4 = ((1.0 - wA) * (1.0 - wB) != 0.0) ? __ldcg(slab + q4) : 0.0;
-                    cin = interp_coldens<true>(c1, c2, c3, c4, wA, wB, p.sig, flags);
+                    cin = interp_coldens<true>(c1, c2, c3, c4, wA, wB, flags);
                 }
                 const double cdho = finish_cell(cin, path, inv_np, flags, nHI_p, strength, pos, p, log2_tab);
                 __stcg(slab + pos, cdho);
@@ -517,20 +522,37 @@ cudaError_t launch_sweep_grid(const SweepParams& p, int ngroups, unsigned* count
 // small preparation kernels
 // ---------------------------------------------------------------------------------------------------
 
-// nHI = ndens * (1 - xh_av) (raytracing.cu:275-276), once per sweep instead of once per (source, cell):
-// halves the scattered loads of the sweep.
+// Cell opacity per unit path in cell units, ntau = ndens * (1 - xh_av) * sigma * dr (raytracing.cu:275-276,311),
+// once per sweep instead of once per (source, cell): halves the scattered loads of the sweep and removes the
+// sigma / dr multiplications from it.
 __global__ void prepare_nhi_kernel(const double* __restrict__ ndens, const double* __restrict__ xh_av,
-                                   double* __restrict__ nhi, int64_t ncell)
+                                   double* __restrict__ ntau, double sig_dr, int64_t ncell)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (int64_t)gridDim.x * blockDim.x)
-        nhi[i] = ndens[i] * (1.0 - xh_av[i]);
+        ntau[i] = (ndens[i] * (1.0 - xh_av[i])) * sig_dr;
 }
 
-cudaError_t launch_prepare_nhi(const double* ndens, const double* xh_av, double* nhi, int64_t ncell, cudaStream_t stream)
+cudaError_t launch_prepare_nhi(const double* ndens, const double* xh_av, double* ntau, double sig_dr, int64_t ncell,
+                               cudaStream_t stream)
 {
     int64_t blocks = (ncell + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    prepare_nhi_kernel<<<(int)blocks, 256, 0, stream>>>(ndens, xh_av, nhi, ncell);
+    prepare_nhi_kernel<<<(int)blocks, 256, 0, stream>>>(ndens, xh_av, ntau, sig_dr, ncell);
+    return cudaGetLastError();
+}
+
+// grid *= factor (debug path: optical depths back to column densities)
+__global__ void scale_grid_kernel(double* __restrict__ grid, double factor, int64_t ncell)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (int64_t)gridDim.x * blockDim.x)
+        grid[i] *= factor;
+}
+
+cudaError_t launch_scale_grid(double* grid, double factor, int64_t ncell, cudaStream_t stream)
+{
+    int64_t blocks = (ncell + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    scale_grid_kernel<<<(int)blocks, 256, 0, stream>>>(grid, factor, ncell);
     return cudaGetLastError();
 }
 
