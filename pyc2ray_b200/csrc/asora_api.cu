@@ -567,6 +567,34 @@ int asora_buffer_upload(int which, const double* host)
     return 0;
 }
 
+// Fortran-ordered host grids: staged through the opacity scratch (rebuilt before every sweep, so free here)
+int asora_buffer_upload_f(int which, const double* host_fortran)
+{
+    if (int rc = need_init()) return rc;
+    if (int rc = ensure_buffer(which)) return rc;
+    if (!host_fortran) return fail("buffer_upload_f: null pointer");
+    if (!g.nhi) CK(cudaMalloc(&g.nhi, sizeof(double) * g.ncell));
+    if (which == ASORA_BUF_TEMP) g.chem_factors_valid = false;
+    CK(cudaMemcpyAsync(g.nhi, host_fortran, sizeof(double) * g.ncell, cudaMemcpyHostToDevice, g.stream));
+    cudaError_t e = launch_reverse_axes(g.nhi, g.buf[which], g.N, g.stream);
+    if (e != cudaSuccess) return fail_cuda("reverse_axes_kernel launch", e);
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+int asora_buffer_download_f(int which, double* host_fortran)
+{
+    if (int rc = need_init()) return rc;
+    if (int rc = ensure_buffer(which)) return rc;
+    if (!host_fortran) return fail("buffer_download_f: null pointer");
+    if (!g.nhi) CK(cudaMalloc(&g.nhi, sizeof(double) * g.ncell));
+    cudaError_t e = launch_reverse_axes(g.buf[which], g.nhi, g.N, g.stream);
+    if (e != cudaSuccess) return fail_cuda("reverse_axes_kernel launch", e);
+    CK(cudaMemcpyAsync(host_fortran, g.nhi, sizeof(double) * g.ncell, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
 int asora_buffer_upload_range(int which, const double* host, int64_t cell_offset, int64_t cell_count)
 {
     if (int rc = need_init()) return rc;

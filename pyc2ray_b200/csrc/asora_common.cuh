@@ -131,6 +131,7 @@ cudaError_t launch_sweep_grid(const SweepParams& p, int ngroups, unsigned* count
 
 cudaError_t launch_prepare_nhi(const double* ndens, const double* xh_av, double* ntau, double sig_dr, int64_t ncell,
                                cudaStream_t stream);
+cudaError_t launch_reverse_axes(const double* in, double* out, int N, cudaStream_t stream);
 cudaError_t launch_scale_grid(double* grid, double factor, int64_t ncell, cudaStream_t stream);
 cudaError_t launch_pair_table(const double* table, double2* pairs, int ntab, cudaStream_t stream);
 void host_log2_table(double* tab512);

@@ -572,3 +572,29 @@ cudaError_t launch_pair_table(const double* table, double2* pairs, int ntab, cud
     pair_table_kernel<<<(ntab + 255) / 256, 256, 0, stream>>>(table, pairs, ntab);
     return cudaGetLastError();
 }
+
+// Axis reversal between Fortran order (i fastest) and the device layout (k fastest): for every j the (i,k) plane is
+// a 2-D transpose.  in[k*N*N + j*N + i] -> out[i*N*N + j*N + k]; applying it twice is the identity, so the same
+// kernel serves both directions.
+__global__ void reverse_axes_kernel(const double* __restrict__ in, double* __restrict__ out, int N)
+{
+    __shared__ double tile[32][33];
+    const int j = blockIdx.z;
+    const int i0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int k = k0 + r, i = i0 + threadIdx.x;
+        if (i < N && k < N) tile[r][threadIdx.x] = in[((size_t)k * N + j) * N + i];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = i0 + r, k = k0 + threadIdx.x;
+        if (i < N && k < N) out[((size_t)i * N + j) * N + k] = tile[threadIdx.x][r];
+    }
+}
+
+cudaError_t launch_reverse_axes(const double* in, double* out, int N, cudaStream_t stream)
+{
+    dim3 grid((N + 31) / 32, (N + 31) / 32, N), block(32, 8);
+    reverse_axes_kernel<<<grid, block, 0, stream>>>(in, out, N);
+    return cudaGetLastError();
+}

@@ -27,6 +27,20 @@ def _flat(a):
     return np.ascontiguousarray(np.ravel(a), dtype=np.float64)
 
 
+def _is_f(a):
+    """Fortran-ordered float64 3-D grid (what the reference's driver classes hold)?"""
+    return (isinstance(a, np.ndarray) and a.ndim == 3 and a.dtype == np.float64 and a.flags.f_contiguous
+            and not a.flags.c_contiguous)
+
+
+def _upload(buf, a):
+    """Whole-grid upload; Fortran-ordered grids go up as they are and are re-ordered on the device."""
+    if _is_f(a):
+        check(L.asora_buffer_upload_f(buf, dptr(a)))
+    else:
+        check(L.asora_buffer_upload(buf, dptr(_flat(a))))
+
+
 def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table, minlogtau, dlogtau, R_max_LLS,
                    convergence_fraction, sig, bh00, albpow, colh0, temph0, abu_c, logfile, quiet, shard=None,
                    group=None, max_iter=10000, decomposition="list"):
@@ -63,10 +77,10 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
     NumSrc = normflux_flat.shape[0]
 
     check(L.asora_source_data_to_device(iptr(srcpos_flat), dptr(normflux_flat), NumSrc))
-    if halo is None:
-        check(L.asora_buffer_upload(_cabi.BUF_NDENS, dptr(_flat(ndens))))
-        check(L.asora_buffer_upload(_cabi.BUF_TEMP, dptr(_flat(temp))))
-        check(L.asora_buffer_upload(_cabi.BUF_XH, dptr(_flat(xh))))
+    if halo is None or _is_f(ndens) or _is_f(temp) or _is_f(xh):
+        _upload(_cabi.BUF_NDENS, ndens)
+        _upload(_cabi.BUF_TEMP, temp)
+        _upload(_cabi.BUF_XH, xh)
     else:
         # a rank only ever reads its own planes and the halos: upload just those (at most two segments)
         first, count = halo.active_range()
@@ -157,13 +171,17 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
         torch.cuda.synchronize()
     if rank == 0:
         printlog("Multiple source convergence reached.", logfile, quiet)
-    xh_new = np.empty(NumCells)
     phi_ion = np.empty(NumCells)
-    check(L.asora_buffer_download(_cabi.BUF_XH_INTERMED, dptr(xh_new)))
     check(L.asora_buffer_download(_cabi.BUF_PHI_ION, dptr(phi_ion)))
-    xh_new = xh_new.reshape(N, N, N)
-    if isinstance(xh, np.ndarray) and xh.flags.f_contiguous and not xh.flags.c_contiguous:
-        xh_new = np.asfortranarray(xh_new)  # np.copy(xh) keeps the order of xh (evolve.py:136-137,244)
+    if _is_f(xh):
+        # np.copy(xh) keeps the order of xh (evolve.py:136-137,244): hand back a Fortran-ordered grid,
+        # re-ordered on the device
+        xh_new = np.empty((N, N, N), order="F")
+        check(L.asora_buffer_download_f(_cabi.BUF_XH_INTERMED, dptr(xh_new)))
+    else:
+        xh_new = np.empty(NumCells)
+        check(L.asora_buffer_download(_cabi.BUF_XH_INTERMED, dptr(xh_new)))
+        xh_new = xh_new.reshape(N, N, N)
     evolve3D.last_niter = niter
     return xh_new, phi_ion.reshape(N, N, N)
 

@@ -29,6 +29,8 @@ SIGNATURES = {
                                ctypes.POINTER(_i)]),
     "asora_device_buffer": (ctypes.c_void_p, [_i]),
     "asora_buffer_upload": (_i, [_i, c_dp]),
+    "asora_buffer_upload_f": (_i, [_i, c_dp]),
+    "asora_buffer_download_f": (_i, [_i, c_dp]),
     "asora_buffer_upload_range": (_i, [_i, c_dp, _i64, _i64]),
     "asora_buffer_download": (_i, [_i, c_dp]),
     "asora_buffer_copy": (_i, [_i, _i]),

@@ -399,3 +399,30 @@ def test_degenerate_inputs(libs, variant):
             _assert_close(phi, ref, f"R={R}")
     finally:
         libasora.device_close()
+
+
+def test_evolve3D_fortran_ordered_grids(libs):
+    """Fortran-ordered inputs (the reference's driver classes: c2ray_test.py:167-169) are re-ordered on the device;
+    the result must equal the C-ordered call and come back Fortran-ordered (evolve.py:136-137,244)."""
+    oracle, p, _cabi, libasora = libs
+    from tests.fields import make_case
+    c = make_case("multi_n32")
+    N = c["N"]
+    rng = np.random.default_rng(11)
+    temp = np.full((N, N, N), 1e4) * rng.uniform(0.8, 1.2, size=(N, N, N))
+    xh0 = rng.uniform(1e-4, 1e-2, size=(N, N, N))
+    chem = (2.59e-13, -0.7, 1.3e-8 * 0.83 / 13.598 ** 2, 13.598 / 8.617e-5, 7.1e-7)
+    args = (True, 1000, 64, 1e-2)
+    tail = (c["thin"], c["thick"], c["minlogtau"], c["dlogtau"], c["R"], 1e-4, c["sig"]) + chem
+    p.device_init(N, 8)
+    try:
+        p.photo_table_to_device(c["thin"], c["thick"])
+        xc, pc = p.evolve3D(3.15576e13, c["dr"], c["flux"] * 1e6, c["srcpos"], *args, temp, c["ndens"], xh0, *tail,
+                            logfile=None, quiet=True)
+        xf, pf = p.evolve3D(3.15576e13, c["dr"], c["flux"] * 1e6, c["srcpos"], *args, np.asfortranarray(temp),
+                            np.asfortranarray(c["ndens"]), np.asfortranarray(xh0), *tail, logfile=None, quiet=True)
+    finally:
+        p.device_close()
+    assert xf.flags.f_contiguous and not xf.flags.c_contiguous and xc.flags.c_contiguous
+    np.testing.assert_allclose(xf, xc, rtol=1e-12, atol=0)
+    _assert_close(pf.ravel(), pc.ravel(), "phi_ion F vs C", rtol=1e-11)
