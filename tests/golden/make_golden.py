@@ -100,6 +100,10 @@ def kat():
         "hackathon_test1_tolerances": {
             "source": "test/unit_tests_hackathon/1_single_black_body/run_test.py:91-115",
             "abs": {"mean": 1e-8, "std": 3e-7, "max": 5e-6}, "rel": {"mean": 1e-7, "std": 3e-6, "max": 2e-5}},
+        "test2_cosmo_Ifront": {
+            "source": "test/paper_tests/test2_Ifront_cosmo/make_plot.ipynb cell 5 (printed output) and cell 9 (plot band)",
+            "age_z9_Myr": 563.9825828256307, "lambda": 0.862007470892602,
+            "cosmology": {"H0": 70, "Om0": 0.27, "Tcmb0": 2.726, "Ob0": 0.043}, "band": [0.985, 1.005]},
         "asora_asymptote_ns_per_source_cell": {
             "source": "test/paper_tests/raytracing_benchmark/plot_sources.ipynb cell 5", "value": 3.1558841065316494e-09},
     }

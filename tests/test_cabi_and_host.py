@@ -249,3 +249,17 @@ def test_slab_decomposition_over_gloo(tmp_path, world):
         assert (xh[edges[r]:edges[r + 1]] == r).all()
         assert (xh[[(edges[r] - k) % N for k in range(1, h + 1)]] == (r - 1) % world).all()
         assert (xh[[(edges[r + 1] + k) % N for k in range(h)]] == (r + 1) % world).all()
+
+
+def test_cosmology_matches_astropy_printed_age():
+    """test/paper_tests/test2_Ifront_cosmo/make_plot.ipynb cell 5 prints astropy's FlatLambdaCDM(70, 0.27, 2.726,
+    Ob0=0.043).age(9) in Myr and lambda = t_i / t_rec; the stand-in must reproduce both."""
+    import json
+    from pyc2ray_b200.cosmology import FlatLambdaCDM
+    k = json.load(open(os.path.join(ROOT, "tests", "golden", "kat.json")))["test2_cosmo_Ifront"]
+    c = FlatLambdaCDM(k["cosmology"]["H0"], k["cosmology"]["Om0"], k["cosmology"]["Tcmb0"], Ob0=k["cosmology"]["Ob0"])
+    myr = 1e6 * 365.25 * 86400.0
+    ti = c.age(9.0) / myr
+    assert abs(ti / k["age_z9_Myr"] - 1.0) < 1e-10
+    t_rec = 1.0 / (2.59e-13 * 1.87e-4 * 3.15576e7 * 1e6)
+    assert abs(ti / t_rec / k["lambda"] - 1.0) < 1e-10
