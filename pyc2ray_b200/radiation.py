@@ -10,7 +10,7 @@ the SED normalised to ``S_star_ref`` photons/s over the integration band.
 import numpy as np
 from scipy.integrate import quad, quad_vec
 
-__all__ = ["make_tau_table", "BlackBodySource", "blackbody_tables", "EV2FR"]
+__all__ = ["make_tau_table", "BlackBodySource", "blackbody_tables", "blackbody_heat_tables", "EV2FR"]
 
 # C2Ray's own constant values (blackbody.py:11-14, c2ray_base.py:76): kept for comparability.
 H_OVER_K = 6.6260755e-27 / 1.381e-16
@@ -18,6 +18,9 @@ _PI = 3.141592654
 _C = 2.997925e+10
 TWO_PI_OVER_C2 = 2.0 * _PI / (_C * _C)
 EV2FR = 0.241838e15
+# heating tables (blackbody.py:3-5,15-16 take these two from astropy: CODATA 2018 values)
+HPLANCK = 6.62607015e-27            # erg s
+ION_FREQ_HI = 10973731.568160 * 2.99792458e8   # Ryd * c in Hz
 
 
 def make_tau_table(minlogtau, maxlogtau, NumTau):
@@ -60,6 +63,14 @@ class BlackBodySource:
         s = self.cross_section_freq_dependence(freq)
         return np.where(tau * s < 700.0, self.SED(freq) * s * np.exp(-tau * s), 0.0)
 
+    def make_heat_table(self, tau, freq_min, freq_max, S_star_ref):
+        """Photo-heating tables: the photo integrands weighted by h (nu - nu_HI) (blackbody.py:55-61,79-85)."""
+        self.normalize_SED(freq_min, freq_max, S_star_ref)
+        w = lambda f: HPLANCK * (f - ION_FREQ_HI)
+        thin = quad_vec(lambda f: w(f) * self._thin(f, tau), freq_min, freq_max, epsrel=1e-12)[0]
+        thick = quad_vec(lambda f: w(f) * self._thick(f, tau), freq_min, freq_max, epsrel=1e-12)[0]
+        return thin, thick
+
     def make_photo_table(self, tau, freq_min, freq_max, S_star_ref):
         self.normalize_SED(freq_min, freq_max, S_star_ref)
         thin = quad_vec(lambda f: self._thin(f, tau), freq_min, freq_max, epsrel=1e-12)[0]
@@ -78,3 +89,12 @@ def blackbody_tables(Teff, grey, minlogtau, maxlogtau, NumTau, pl_index=2.8, eth
     src = BlackBodySource(Teff, grey, f_lo, pl_index)
     thin, thick = src.make_photo_table(tau, f_lo, f_hi, 1e48)
     return thin, thick, dlogtau
+
+
+def blackbody_heat_tables(Teff, grey, minlogtau, maxlogtau, NumTau, pl_index=2.8, eth0=13.598, ethe1=54.416):
+    """Heating tables as C2Ray._radiation_init builds them when compute_heating_rates is set
+    (c2ray_base.py:419-432).  Returns (heat_thin, heat_thick)."""
+    tau, _ = make_tau_table(minlogtau, maxlogtau, NumTau)
+    f_lo = EV2FR * eth0
+    f_hi = 10 * EV2FR * ethe1
+    return BlackBodySource(Teff, grey, f_lo, pl_index).make_heat_table(tau, f_lo, f_hi, 1e48)

@@ -72,6 +72,18 @@ def ref_tables():
     print("ref_tables.npz", {k: v.shape for k, v in out.items()})
 
 
+def ref_heat_tables():
+    _stub_astropy()
+    common = _load(os.path.join(REF, "pyc2ray/radiation/common.py"), "ref_common")
+    bb = _load(os.path.join(REF, "pyc2ray/radiation/blackbody.py"), "ref_blackbody")
+    ev2fr, eth0, ethe1 = 0.241838e15, 13.598, 54.416
+    tau, _ = common.make_tau_table(-20.0, 4.0, 2000)
+    src = bb.BlackBodySource(5e4, 0, ev2fr * eth0, 2.8)
+    thin, thick = src.make_heat_table(tau, ev2fr * eth0, 10 * ev2fr * ethe1, 1e48)
+    np.savez_compressed(os.path.join(HERE, "ref_heat_tables.npz"), bb5e4_heat_thin=thin, bb5e4_heat_thick=thick)
+    print("ref_heat_tables.npz", thin.shape, thin[:2], thick[:2])
+
+
 def ref_sources():
     su = _load(os.path.join(REF, "pyc2ray/utils/sourceutils.py"), "ref_sourceutils")
     tmp = "/tmp/_golden_src.txt"
@@ -129,7 +141,11 @@ def oracle_vectors():
 
 
 if __name__ == "__main__":
+    if "heat" in sys.argv[1:]:
+        ref_heat_tables()
+        sys.exit(0)
     ref_tables()
+    ref_heat_tables()
     ref_sources()
     kat()
     oracle_vectors()
