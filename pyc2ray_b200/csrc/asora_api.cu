@@ -23,18 +23,21 @@ struct Context {
     int device = 0;
     int sm_count = 0;
     int smem_optin = 0;
+    int smem_per_sm = 0;
     cudaStream_t stream = nullptr;      // the stream work is queued on
     cudaStream_t own_stream = nullptr;  // created by device_init; `stream` unless the caller set one
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double* buf[ASORA_BUF_COUNT] = {nullptr};
     double2* thin = nullptr;   // {T[i], T[i+1]-T[i]} pairs (sweep_kernels.cu: photo_lookup)
     double2* thick = nullptr;
+    cudaTextureObject_t tex_pairs = 0;  // one allocation: thick pairs, then thin pairs
     int ntab = 0;
     double* grid_scratch = nullptr;  // ngroups x N^3 column densities of the grid-cooperative sweep
     int grid_scratch_groups = 0;
     int grid_max_groups = 0;
     unsigned* grid_counters = nullptr;
-    double* nhi = nullptr;      // ndens * (1 - xh_av), rebuilt before every sweep
+    double* nhi = nullptr;      // ndens * (1 - xh_av) * sigma * dr, rebuilt before every sweep
+    double* phi_keep = nullptr; // rates of earlier sweeps while a sweep accumulates on top of them (zero_phi = 0)
     double2* log2_tab = nullptr;
     int* src_pos = nullptr;      // as uploaded (positions reduced modulo N)
     double* src_flux = nullptr;
@@ -55,7 +58,7 @@ struct Context {
     int64_t chem_stage_n = 0;
     // stats of the last sweep
     int variant_forced = 0;
-    int tune_S = 0, tune_block = 0, tune_regs = 0;
+    int tune_S = 0, tune_block = 0, tune_opts = 0;
     int tune_parts = 0;
     int slab_begin = 0, slab_count = 0;  // active planes of a slab-decomposed run (0 = whole grid)
     int sphere_only = 0;
@@ -90,6 +93,14 @@ int fail_cuda(const char* where, cudaError_t e)
         cudaError_t _e = (call);                          \
         if (_e != cudaSuccess) return fail_cuda(#call, _e); \
     } while (0)
+
+void free_tables()
+{
+    if (g.tex_pairs) cudaDestroyTextureObject(g.tex_pairs);
+    g.tex_pairs = 0;
+    if (g.thick) cudaFree(g.thick);  // one allocation holds both tables
+    g.thin = g.thick = nullptr;
+}
 
 int need_init()
 {
@@ -152,6 +163,7 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
         host_log2_table(h);
         CK(cudaMalloc(&g.log2_tab, sizeof(h)));
         CK(cudaMemcpy(g.log2_tab, h, sizeof(h), cudaMemcpyHostToDevice));
+        CK(upload_inv_levels());
     }
 
     SweepParams p;
@@ -170,6 +182,14 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     // rates.cu:77-78 clamps: tau >= 1e-20, 0 <= index <= NumTau  <=>  tau_lo <= tau <= tau_hi
     p.tau_lo = std::max(1.0e-20, std::pow(10.0, minlogtau - dlogtau));
     p.tau_hi = std::pow(10.0, minlogtau + ((double)NumTau - 1.0) * dlogtau);
+    {   // fast range test of photo_lookup: high words strictly between those of tau_lo and tau_hi
+        uint64_t blo, bhi;
+        std::memcpy(&blo, &p.tau_lo, 8);
+        std::memcpy(&bhi, &p.tau_hi, 8);
+        const int hlo = (int)(blo >> 32) + 1, hhi = (int)(bhi >> 32);  // [hlo, hhi) is safe
+        p.hi_min = hlo;
+        p.hi_span = hhi > hlo ? (unsigned)(hhi - hlo) : 0u;
+    }
     p.minlogtau = minlogtau;
     p.dlogtau = dlogtau;
     p.NumTau = NumTau;
@@ -179,6 +199,7 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     p.phi_ion = g.buf[ASORA_BUF_PHI_ION];
     p.thin = g.thin;
     p.thick = g.thick;
+    p.tex_pairs = g.tex_pairs;
     // a sweep over the whole list may take the sources in any order (phi_ion is a sum)
     const bool whole = (begin == 0 && count == g.nsrc && g.src_pos_sorted != nullptr);
     p.src_pos = whole ? g.src_pos_sorted : g.src_pos;
@@ -201,7 +222,7 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
 
     // Variant selection: the shared-memory sweep needs two levels of column densities per source.
     int variant = g.variant_forced;
-    int S = 1, block = 256;
+    int S = 1, block = 256, opts = 0;
     bool plan_ok = false;
     if (variant != 2) {
         const int lo_side = 2 * std::min(p.q_max, std::max(-p.last_l, p.last_r)) + 1;
@@ -221,13 +242,13 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
                     }
                 }
                 if (g.tune_parts > 0 || parts == 8) break;
-                if (sweep_smem_bytes(g.plan, 1) <= (size_t)g.smem_optin) break;
+                if (sweep_smem_bytes(g.plan, 1, 1) <= (size_t)g.smem_optin) break;
                 parts *= 2;
             }
             plan_ok = g.plan.valid;
         }
         if (plan_ok) {
-            const size_t per_src = sweep_smem_bytes(g.plan, 1);
+            const size_t per_src = sweep_smem_bytes(g.plan, 1, 1);
             const size_t budget = (size_t)g.smem_optin;
             if (per_src > budget) {
                 plan_ok = false;
@@ -238,9 +259,20 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
                 // resident CTAs.
                 const int maxc = g.plan.max_level_cells;
                 block = maxc < 2048 ? 256 : (2 * per_src <= budget ? 512 : 1024);
-                S = (block == 256 && count >= 8 * g.sm_count && 3 * sweep_smem_bytes(g.plan, 2) <= budget) ? 2 : 1;
+                S = (block == 256 && count >= 8 * g.sm_count && 3 * sweep_smem_bytes(g.plan, 2, 1) <= budget) ? 2 : 1;
                 if (g.tune_S > 0 && (size_t)g.tune_S * per_src <= budget) S = g.tune_S;
                 if (g.tune_block > 0) block = g.tune_block;
+                // eight bank-staggered copies of the log2 table (28 KB more) when they do not cost a resident CTA
+                const int want = block >= 1024 ? 1 : (block == 512 ? 2 : 4);
+                const size_t per_sm = (size_t)g.smem_per_sm;
+                const size_t with8 = sweep_smem_bytes(g.plan, S, 8) + 1024;
+                opts = (with8 <= budget && want * with8 <= per_sm) ? 1 : 0;
+                // table gathers through the texture pipe: always (R = 30: 18.9 -> 18.2 ms; R = 10.76: 1.25 -> 1.21 ms);
+                // offsets word one cell ahead: only the small-radius shape gains (R = 10.76, two sources x 256
+                // threads: 1.21 -> 1.11 ms; R = 30, 1024 threads: 18.2 -> 18.9 ms) -- scripts/perf_probe6.py
+                opts |= 2;
+                if (block == 256) opts |= 4;
+                opts ^= g.tune_opts;  // profiling knob: bits 16-18 of set_tuning's block_threads toggle the options
             }
         }
         if (variant == 1 && !plan_ok) return fail("sweep variant 1 forced but a level does not fit in shared memory");
@@ -292,18 +324,41 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
                                                g.nhi + seg_off[sg], sig * dr, seg_len[sg], g.stream);
             if (e != cudaSuccess) return fail_cuda("prepare_nhi_kernel launch", e);
             g.last_launches += 1;
-            if (zero_phi)
-                CK(cudaMemsetAsync(g.buf[ASORA_BUF_PHI_ION] + seg_off[sg], 0, sizeof(double) * seg_len[sg], g.stream));
+            // the sweep accumulates undivided sums in phi_ion (finish_cell); earlier rates wait in phi_keep
+            if (!zero_phi) {
+                if (!g.phi_keep) CK(cudaMalloc(&g.phi_keep, sizeof(double) * g.ncell));
+                CK(cudaMemcpyAsync(g.phi_keep + seg_off[sg], g.buf[ASORA_BUF_PHI_ION] + seg_off[sg],
+                                   sizeof(double) * seg_len[sg], cudaMemcpyDeviceToDevice, g.stream));
+            }
+            CK(cudaMemsetAsync(g.buf[ASORA_BUF_PHI_ION] + seg_off[sg], 0, sizeof(double) * seg_len[sg], g.stream));
         }
     }
 
     if (variant == 1) {
         g.last_levels = g.plan.nlevels;
-        cudaError_t e = launch_sweep_smem(g.plan, p, S, block, g.tune_regs, g.stream, &g.last_launches);
+        cudaError_t e = launch_sweep_smem(g.plan, p, S, block, opts, g.stream, &g.last_launches);
         if (e != cudaSuccess) return fail_cuda("sweep_smem_kernel launch", e);
     } else {
         cudaError_t e = launch_sweep_grid(p, groups, g.grid_counters, g.stream, &g.last_launches, &g.last_levels);
         if (e != cudaSuccess) return fail_cuda("sweep_grid_kernel launch", e);
+    }
+    {   // phi = sum / ntau over the planes the sweep could touch
+        const int64_t plane = (int64_t)N * N;
+        int64_t seg_off[2] = {0, 0}, seg_len[2] = {g.ncell, 0};
+        if (g.slab_count > 0 && g.slab_count < N) {
+            const int b = ((g.slab_begin % N) + N) % N;
+            const int first = std::min(g.slab_count, N - b);
+            seg_off[0] = b * plane;
+            seg_len[0] = first * plane;
+            seg_len[1] = (g.slab_count - first) * plane;
+        }
+        for (int sg = 0; sg < 2; sg++) {
+            if (seg_len[sg] <= 0) continue;
+            cudaError_t e = launch_finish_phi(g.buf[ASORA_BUF_PHI_ION] + seg_off[sg], g.nhi + seg_off[sg],
+                                              zero_phi ? nullptr : g.phi_keep + seg_off[sg], seg_len[sg], g.stream);
+            if (e != cudaSuccess) return fail_cuda("finish_phi_kernel launch", e);
+            g.last_launches += 1;
+        }
     }
     if (coldens_grid) {
         // the kernels store optical depths; the debug interface promises column densities
@@ -335,6 +390,7 @@ int asora_device_init(int N, int num_src_par)
     if (prop.major < 10) return fail(std::string("device_init: ") + prop.name + " is not an sm_100 class GPU");
     g.sm_count = prop.multiProcessorCount;
     CK(cudaDeviceGetAttribute(&g.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, g.device));
+    CK(cudaDeviceGetAttribute(&g.smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, g.device));
     g.N = N;
     g.ncell = (int64_t)N * N * N;
     CK(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
@@ -366,9 +422,10 @@ int asora_device_close(void)
         if (g.buf[i]) cudaFree(g.buf[i]);
         g.buf[i] = nullptr;
     }
-    if (g.thin) cudaFree(g.thin);
-    if (g.thick) cudaFree(g.thick);
+    free_tables();
     if (g.nhi) cudaFree(g.nhi);
+    if (g.phi_keep) cudaFree(g.phi_keep);
+    g.phi_keep = nullptr;
     if (g.grid_scratch) cudaFree(g.grid_scratch);
     if (g.grid_counters) cudaFree(g.grid_counters);
     g.grid_scratch = nullptr;
@@ -424,13 +481,11 @@ int asora_photo_table_to_device(const double* thin_table, const double* thick_ta
 {
     if (int rc = need_init()) return rc;
     if (NumTau < 2 || !thin_table || !thick_table) return fail("photo_table_to_device: bad arguments");
-    if (g.thin) cudaFree(g.thin);
-    if (g.thick) cudaFree(g.thick);
-    g.thin = g.thick = nullptr;
+    free_tables();
     double* raw = nullptr;
     CK(cudaMalloc(&raw, sizeof(double) * 2 * (size_t)NumTau));
-    CK(cudaMalloc(&g.thin, sizeof(double2) * NumTau));
-    CK(cudaMalloc(&g.thick, sizeof(double2) * NumTau));
+    CK(cudaMalloc(&g.thick, sizeof(double2) * 2 * (size_t)NumTau));
+    g.thin = g.thick + NumTau;
     CK(cudaMemcpyAsync(raw, thin_table, sizeof(double) * NumTau, cudaMemcpyHostToDevice, g.stream));
     CK(cudaMemcpyAsync(raw + NumTau, thick_table, sizeof(double) * NumTau, cudaMemcpyHostToDevice, g.stream));
     cudaError_t e = launch_pair_table(raw, g.thin, NumTau, g.stream);
@@ -439,6 +494,18 @@ int asora_photo_table_to_device(const double* thin_table, const double* thick_ta
     CK(cudaStreamSynchronize(g.stream));
     cudaFree(raw);
     g.ntab = NumTau;
+    {
+        cudaResourceDesc rd;
+        std::memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = (void*)g.thick;
+        rd.res.linear.desc = cudaCreateChannelDesc<int4>();
+        rd.res.linear.sizeInBytes = sizeof(double2) * 2 * (size_t)NumTau;
+        cudaTextureDesc td;
+        std::memset(&td, 0, sizeof(td));
+        td.readMode = cudaReadModeElementType;
+        CK(cudaCreateTextureObject(&g.tex_pairs, &rd, &td, nullptr));
+    }
     return 0;
 }
 
@@ -742,8 +809,9 @@ int asora_set_sphere_only(int sphere_only)
 
 int asora_set_tuning(int sources_per_cta, int block_threads)
 {
-    // bit 16 of block_threads selects the relaxed register mode (profiling knob)
-    g.tune_regs = (block_threads >> 16) & 1;
+    // bits 16-18 of block_threads toggle launch options of the shared-memory sweep (profiling knob): 16 = copies of
+    // the log2 table, 17 = table gathers through the texture pipe, 18 = offsets word fetched one cell ahead
+    g.tune_opts = (block_threads >> 16) & 7;
     g.tune_parts = (block_threads >> 20) & 15; // bits 20-23: parts per source (1, 2, 4, 8), 0 = automatic
     block_threads &= 0xffff;
     if (!(sources_per_cta == 0 || sources_per_cta == 1 || sources_per_cta == 2 || sources_per_cta == 4))

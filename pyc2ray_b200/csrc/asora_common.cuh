@@ -30,7 +30,7 @@
 #define PC_DIAG2 4u   // incoming column scaled by sqrt(2) (raytracing.cu:431-441)
 #define PC_DIAG3 8u   // incoming column scaled by sqrt(3)
 
-// One cell of the sweep plan (48 bytes, three 16-byte loads).
+// One cell of the sweep plan on the host (48 bytes); the device copy keeps 32 of them (two 16-byte streams).
 struct __align__(16) PlanCell {
     double wA, wB;   // |minor offset| / |dominant offset| for the two minor axes
     double path;     // path length through the cell in cell units (raytracing.cu:444,489,533)
@@ -39,7 +39,7 @@ struct __align__(16) PlanCell {
     uint16_t nb[4];  // slots, in the previous level, of the 4 upstream cells c1..c4
     uint8_t d[3];    // offset from the source, biased by -plan.lo (index into the per-source wrap tables)
     uint8_t flags;
-    uint32_t pad;
+    uint32_t ab;     // |minor A| | |minor B| << 8: wA = a/m, wB = b/m are rebuilt on the device (m = level = |dominant|)
 };
 static_assert(sizeof(PlanCell) == 48, "PlanCell must be 48 bytes");
 
@@ -55,10 +55,11 @@ struct SweepPlan {
     int64_t ncells = 0;                // plan entries (all parts; bounding planes appear once per part)
     std::vector<int> level_start;      // [parts][nlevels+1], absolute entry offsets
     std::vector<PlanCell> cells;       // level-major, lexicographic (di,dj,dk) inside a level
-    // device copy, split into three 16-byte streams (structure of arrays): a warp's LDG.128 then covers 4
-    // contiguous 128-byte lines instead of 12 lines of a 48-byte-strided array of structures -- the L1/LSU
-    // wavefront pipe was the busiest unit of the sweep (82 % in profiles/r01c_sweep_smem_R30.txt)
-    int4* d_cells = nullptr;           // [3][ncells]: {wA,wB} | {path,inv_np} | {nb[4],d[3],flags,pad}
+    // device copy, split into two 16-byte streams (structure of arrays): a warp's LDG.128 then covers 4
+    // contiguous 128-byte lines instead of the lines of a strided array of structures -- the L1/LSU
+    // wavefront pipe is the busiest unit of the sweep (profiles/r01c, r01f)
+    int4* d_cells = nullptr;           // [2][ncells]: {path,inv_np} | {nb[4],d[3],flags,ab}
+    unsigned* d_dwords = nullptr;      // [ncells]: {d[3],flags} once more as a 4-byte stream (one-cell-ahead fetch)
     int* d_level_start = nullptr;
     bool valid = false;
 };
@@ -74,6 +75,8 @@ struct SweepParams {
     double tau_max;           // sigma * MAX_COLDENSH: no rate beyond this incoming optical depth (raytracing.cu:315)
     double lut_a, lut_b;      // table index = lut_a + lut_b * log2(tau)  (rates.cu:77-78)
     double tau_lo, tau_hi;    // optical depths at which that index reaches 0 (>= 1e-20) and NumTau
+    int hi_min;               // high words of a double in [hi_min, hi_min + hi_span) are strictly inside (tau_lo, tau_hi)
+    unsigned hi_span;
     double minlogtau, dlogtau;
     int NumTau;               // index clamp as passed by the caller (rates.cu:78-79)
     int ntab;                 // uploaded table length
@@ -81,6 +84,7 @@ struct SweepParams {
     double* phi_ion;
     const double2* thin;      // {T[i], T[i+1]-T[i]} pairs of the uploaded tables
     const double2* thick;
+    cudaTextureObject_t tex_pairs;  // both pair tables as int4 texels: thick at [0, ntab), thin at [ntab, 2 ntab)
     const double2* log2_tab;  // 256 x {1/c_j, log2 c_j}, c_j the centre of mantissa bin j
     const int* src_pos;
     const double* src_flux;
@@ -92,19 +96,18 @@ struct SweepParams {
 
 // ---- fp64 helpers shared by the device code ----------------------------------------------------------
 #ifdef __CUDACC__
-// 1/x for a normal, finite x: MUFU.RCP64H seed (>= 20 bits) + one cubic and one quadratic Newton step.
+// 1/x for a normal, finite x: the MUFU.RCP64H seed reads the upper 32 bits of x (relative error < 2^-19) and one
+// cubic step r (1 + e + e^2), e = 1 - x r, brings it below 2^-57; the result is within one ulp.
 __device__ __forceinline__ double fast_rcp(double x)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
     double e = fma(-x, r, 1.0);
     e = fma(e, e, e);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
     return fma(r, e, r);
 }
 
-// a/b with a final residual correction (<= 1 ulp for normal operands)
+// a/b with a final residual correction (<= 1 ulp for normal operands); used by the chemistry
 __device__ __forceinline__ double fast_div(double a, double b)
 {
     const double r = fast_rcp(b);
@@ -122,19 +125,21 @@ int64_t asora_count_rated_cells(int N, double R, double dr);
 void free_sweep_plan(SweepPlan& plan);
 
 // launchers implemented in sweep_kernels.cu
-size_t sweep_smem_bytes(const SweepPlan& plan, int sources_per_cta);
+size_t sweep_smem_bytes(const SweepPlan& plan, int sources_per_cta, int log2_copies);
 cudaError_t launch_sweep_smem(const SweepPlan& plan, const SweepParams& p, int sources_per_cta, int block,
-                              int regs_mode, cudaStream_t stream, int* launches);
+                              int opts, cudaStream_t stream, int* launches);
 int sweep_grid_groups(const SweepParams& p, int max_groups, int* total_ctas_out, int* group_ctas_out);
 cudaError_t launch_sweep_grid(const SweepParams& p, int ngroups, unsigned* counters, cudaStream_t stream,
                               int* launches, int* levels);
 
 cudaError_t launch_prepare_nhi(const double* ndens, const double* xh_av, double* ntau, double sig_dr, int64_t ncell,
                                cudaStream_t stream);
+cudaError_t launch_finish_phi(double* phi, const double* ntau, const double* keep, int64_t ncell, cudaStream_t stream);
 cudaError_t launch_reverse_axes(const double* in, double* out, int N, cudaStream_t stream);
 cudaError_t launch_scale_grid(double* grid, double factor, int64_t ncell, cudaStream_t stream);
 cudaError_t launch_pair_table(const double* table, double2* pairs, int ntab, cudaStream_t stream);
 void host_log2_table(double* tab512);
+cudaError_t upload_inv_levels();
 
 // chemistry.cu
 cudaError_t launch_temperature_factors(const double* temp, double2* factors, double bh00, double albpow, double colh0,

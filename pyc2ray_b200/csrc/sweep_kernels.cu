@@ -38,6 +38,18 @@ namespace cg = cooperative_groups;
 // Polynomial coefficients live in the constant bank so that DFMA reads them as c[][] operands instead of
 // materialising each 64-bit immediate with two UMOVs (6.7 % of the issued instructions in r01b).
 // log2(1+r) = r * (K[0] + K[1] r + ... + K[5] r^5), K[k] = (-1)^k / ((k+1) ln 2)
+// 1/m for the Chebyshev levels m = 1..255 (entry 0 is 0): a constant-bank operand the compiler can re-read instead
+// of holding it in registers across the cell loop
+__constant__ double kInvLevel[256];
+
+cudaError_t upload_inv_levels()
+{
+    double h[256];
+    h[0] = 0.0;
+    for (int m = 1; m < 256; m++) h[m] = 1.0 / (double)m;
+    return cudaMemcpyToSymbol(kInvLevel, h, sizeof(h));
+}
+
 __constant__ double kLog2Poly[6] = {1.44269504088896341, -0.72134752044448170, 0.48089834696298783,
                                     -0.36067376022224085, 0.28853900817779268, -0.24044917348149391};
 
@@ -58,12 +70,16 @@ __device__ __forceinline__ double dmin(double a, double b)
     return r;
 }
 
-// log2(x), x normal and positive.  tab[j] = {1/c_j, log2 c_j} for the 256 mantissa bins of [1,2).
-__device__ __forceinline__ double fast_log2(double x, const double2* __restrict__ tab)
+// log2(x), x normal and positive.  tab[j * REP] = {1/c_j, log2 c_j} for the 256 mantissa bins of [1,2).
+// REP = 8: the caller passes tab + (lane & 7) and the table is stored eight times, entry j of copy r at
+// 16-byte word 8 j + r.  The eight lanes an LDS.128 serves per cycle then always hit eight different bank
+// groups; with a single copy the scattered mantissa bins of a warp cost ~11 shared-memory wavefronts per
+// lookup instead of 4 (profiles/r01f: 0.67e9 excess wavefronts, the L1 data pipe being the busiest unit).
+template <int REP>
+__device__ __forceinline__ double fast_log2(int hi, int lo, const double2* __restrict__ tab)
 {
-    const int hi = __double2hiint(x), lo = __double2loint(x);
     const int e = (hi >> 20) - 1023;
-    const double2 t = tab[(hi >> 12) & 0xff];
+    const double2 t = tab[((hi >> 12) & 0xff) * REP];
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
     const double r = fma(m, t.x, -1.0);  // |r| <= 2^-9
     double p = fma(r, kLog2Poly[5], kLog2Poly[4]);
@@ -88,21 +104,62 @@ void host_log2_table(double* tab512)
 // per-cell arithmetic
 // ---------------------------------------------------------------------------------------------------
 
+// Out-of-range optical depths (tau < tau_lo: only the source cell and fully ionised paths; tau > tau_hi:
+// beyond the table): a real call, so that the compiler keeps it out of the predicated fast path.
+__device__ __noinline__ double clamp_tau_slow(double tau, double lo, double hi) { return fmin(fmax(tau, lo), hi); }
+
 // rates.cu:70-83.  The reference clamps tau from below at 1e-20 and the table index to [0, NumTau];
 // here tau itself is clamped to [tau_lo, tau_hi], the optical depths at which the index reaches those
 // bounds (tau_lo >= 1e-20), so index = lut_a + lut_b*log2(tau) needs no further clamping beyond the
 // integer guard against the uploaded table length (reference bug N6: Python callers pass NumTau =
 // table length, which lets i1 reach one element past the table; the pair table's last slope is 0).
-__device__ __forceinline__ double photo_lookup(const double2* __restrict__ pairs, double tau, const SweepParams& p,
-                                               const double2* __restrict__ log2_tab)
+// The range test is one unsigned compare on the high word (positive doubles order like integers): high
+// words in [hi_min, hi_min + hi_span) are strictly inside (tau_lo, tau_hi).
+struct TableIndex {
+    int i0;
+    double residual;
+};
+
+template <int REP>
+__device__ __forceinline__ TableIndex table_index(int hi, int lo, const SweepParams& p, const double2* __restrict__ log2_tab)
 {
-    const double t_c = dmin(dmax(tau, p.tau_lo), p.tau_hi);
-    const double real_i = fma(p.lut_b, fast_log2(t_c, log2_tab), p.lut_a);
-    int i0 = (int)real_i;
-    const double residual = real_i - (double)i0;
-    i0 = max(0, min(i0, p.ntab - 1));
-    const double2 t = __ldg(pairs + i0);
-    return fma(residual, t.y, t.x);
+    const double real_i = fma(p.lut_b, fast_log2<REP>(hi, lo, log2_tab), p.lut_a);
+    TableIndex t;
+    t.i0 = (int)real_i;
+    t.residual = real_i - (double)t.i0;
+    t.i0 = max(0, min(t.i0, p.ntab - 1));
+    return t;
+}
+
+// The two lookups of a rated cell, T_thick(tau_in) and T_out(tau_out), with one shared (rarely taken) range
+// branch so that their logarithms and table loads overlap.
+// TEX: the two 16-byte gathers go through the texture pipe (tex1Dfetch) instead of LDG: a warp's 32 scattered
+// table pairs cost ~20 wavefronts on the LSU data pipe, the busiest unit of the sweep.
+template <int REP, bool TEX>
+__device__ __forceinline__ void photo_lookup2(bool thick, double tau_in, double tau_out, const SweepParams& p,
+                                              const double2* __restrict__ log2_tab, double& t_in, double& t_out)
+{
+    int h1 = __double2hiint(tau_in), h2 = __double2hiint(tau_out);
+    if (__builtin_expect(((unsigned)(h1 - p.hi_min) >= p.hi_span) | ((unsigned)(h2 - p.hi_min) >= p.hi_span), 0)) {
+        tau_in = clamp_tau_slow(tau_in, p.tau_lo, p.tau_hi);
+        tau_out = clamp_tau_slow(tau_out, p.tau_lo, p.tau_hi);
+        h1 = __double2hiint(tau_in);
+        h2 = __double2hiint(tau_out);
+    }
+    const TableIndex a = table_index<REP>(h1, __double2loint(tau_in), p, log2_tab);
+    const TableIndex b = table_index<REP>(h2, __double2loint(tau_out), p, log2_tab);
+    if (TEX) {
+        // one texture over both tables (thick first): a per-lane choice of texture handle would need branches
+        const int4 ua = tex1Dfetch<int4>(p.tex_pairs, a.i0);
+        const int4 ub = tex1Dfetch<int4>(p.tex_pairs, b.i0 + (thick ? 0 : p.ntab));
+        t_in = fma(a.residual, __hiloint2double(ua.w, ua.z), __hiloint2double(ua.y, ua.x));
+        t_out = fma(b.residual, __hiloint2double(ub.w, ub.z), __hiloint2double(ub.y, ub.x));
+    } else {
+        const double2 ta = __ldg(p.thick + a.i0);
+        const double2 tb = __ldg((thick ? p.thick : p.thin) + b.i0);
+        t_in = fma(a.residual, ta.y, ta.x);
+        t_out = fma(b.residual, tb.y, tb.x);
+    }
 }
 
 // raytracing.cu:405-441 with s1..s4 written in terms of the minor-axis fractions (sweep_plan.cu) and
@@ -112,7 +169,9 @@ __device__ __forceinline__ double photo_lookup(const double2* __restrict__ pairs
 // for those corners, so force them to 0; the plan-driven sweep instead points them at a live slot.
 // The kernels work in optical-depth units: every stored column is tau = sigma * N_HI (the pre-pass folds sigma and
 // dr into the per-cell opacity), so c_i * sigma of the reference is the stored value itself.
-template <bool MASK>
+// DIAG: only the 20 edge / corner neighbours of the source (level 1) carry the sqrt(2), sqrt(3) factors of
+// raytracing.cu:431-441; the level loop of the shared-memory sweep compiles them out for levels >= 2.
+template <bool MASK, bool DIAG>
 __device__ __forceinline__ double interp_coldens(double c1, double c2, double c3, double c4, double wA,
                                                  double wB, unsigned flags)
 {
@@ -132,13 +191,14 @@ __device__ __forceinline__ double interp_coldens(double c1, double c2, double c3
     double den = (w1 + w2) + (w3 + w4);
     double cdensi;
     if (den < 1e300) {
-        cdensi = fast_div(fma(c1, w1, c2 * w2) + fma(c3, w3, c4 * w4), den);
+        cdensi = (fma(c1, w1, c2 * w2) + fma(c3, w3, c4 * w4)) * fast_rcp(den);
     } else {  // the products overflowed (optical depths beyond 1e90): the reference's literal form
         w1 = s1 / m1, w2 = s2 / m2, w3 = s3 / m3, w4 = s4 / m4;
         cdensi = (c1 * w1 + c2 * w2 + c3 * w3 + c4 * w4) / (w1 + w2 + w3 + w4);
     }
-    // only the 20 edge / corner neighbours of the source (level 1): a real, almost never taken branch
-    if (__builtin_expect((flags & (PC_DIAG2 | PC_DIAG3)) != 0, 0)) cdensi *= (flags & PC_DIAG3) ? ASORA_SQRT3 : ASORA_SQRT2;
+    if (DIAG) {
+        if ((flags & (PC_DIAG2 | PC_DIAG3)) != 0) cdensi *= (flags & PC_DIAG3) ? ASORA_SQRT3 : ASORA_SQRT2;
+    }
     return cdensi;
 }
 
@@ -154,25 +214,24 @@ __device__ __forceinline__ int wrap(int i, int N)
 //   tau_out  = tau_in + ntau * path        sigma * (coldensh_in + nHI * path * dr)          (raytracing.cu:311)
 //   phi      = strength / Vfact * absorbed / nHI = strength * inv_np * kpref * absorbed / ntau,
 //              kpref = sigma * dr / (4 pi dr^3)                                   (rates.cu:24, raytracing.cu:324)
-// Returns the outgoing optical depth.
+// The division by ntau is the same for every source that reaches the cell, so the sweep accumulates
+// strength * kpref * inv_np * absorbed and one pass over the grid divides afterwards (finish_phi_kernel):
+// sk = strength * kpref.  Returns the outgoing optical depth.
+template <int REP, bool TEX>
 __device__ __forceinline__ double finish_cell(double tau_in, double path_cells, double inv_np, unsigned flags,
-                                              double ntau_p, double strength, size_t pos, const SweepParams& p,
+                                              double ntau_p, double sk, size_t pos, const SweepParams& p,
                                               const double2* __restrict__ log2_tab)
 {
     const double tau_out = fma(ntau_p, path_cells, tau_in);
     if ((flags & PC_RATED) && tau_in <= p.tau_max) {  // coldensh_in <= MAX_COLDENSH (raytracing.cu:315)
         const double dtau = tau_out - tau_in;
         const bool thick = fabs(dtau) > ASORA_TAU_PHOTO_LIMIT;
-        const double t_in = photo_lookup(p.thick, tau_in, p, log2_tab);
-        const double t_out = photo_lookup(thick ? p.thick : p.thin, tau_out, p, log2_tab);
+        double t_in, t_out;
+        photo_lookup2<REP, TEX>(thick, tau_in, tau_out, p, log2_tab, t_in, t_out);
         // rates.cu:28-38: thick cells absorb T(tau_in) - T(tau_out), thin cells dtau * T_thin(tau_out)
         const double absorbed = thick ? (t_in - t_out) : dtau * t_out;
-        const double num = (strength * (inv_np * p.kpref)) * absorbed;
-        // nHI == 0 (fully ionised input cell) divides by zero in the reference too (raytracing.cu:324); the
-        // reciprocal-based division is only used where its flush-to-zero seed is safe
-        const double phi = (ntau_p > 1e-290 && ntau_p < 1e290) ? fast_div(num, ntau_p) : num / ntau_p;
         // one fire-and-forget fp64 reduction per rated (source, cell) pair: RED.E.ADD.F64 at L2
-        atomicAdd(p.phi_ion + pos, phi);
+        atomicAdd(p.phi_ion + pos, (sk * inv_np) * absorbed);
     }
     return tau_out;
 }
@@ -180,7 +239,7 @@ __device__ __forceinline__ double finish_cell(double tau_in, double path_cells, 
 // ---------------------------------------------------------------------------------------------------
 // variant 1: shared-memory level sweep, S sources per CTA
 // ---------------------------------------------------------------------------------------------------
-// One plan cell with its per-source grid positions and neutral densities already fetched.
+// One plan cell with its per-source grid positions and opacities already fetched.
 template <int S>
 struct Fetched {
     double wA, wB, path, inv_np;
@@ -190,50 +249,101 @@ struct Fetched {
     double nhi[S];
 };
 
+// Plan cell: two coalesced 16-byte read-only loads, shared by the S sources of the CTA.  The interpolation
+// fractions wA = a/m, wB = b/m are rebuilt from the byte-sized offsets: the dominant offset of every cell of
+// Chebyshev level m is m itself, so 1/m is a per-level constant and one correction step gives the correctly
+// rounded quotient (verified exhaustively for 0 <= a <= m <= 255) -- 8 arithmetic instructions instead of a
+// third 512-byte load per warp on the L1 data pipe.
 // wrapX/Y/Z: per-source shared-memory tables, indexed by the biased offset, holding the periodic
 // cell coordinate already multiplied by its stride (N*N, N, 1): one LDS per axis replaces the
 // add / sign-fix / compare / select chain of modulo_gpu (raytracing.cu:24,270-272).
-template <int S>
-__device__ __forceinline__ void fetch_cell(Fetched<S>& f, const int4* __restrict__ plan, int ncells, int e,
-                                           const unsigned* __restrict__ wrap_tab, int side,
+// PF: `dword` ({d[3], flags}, the third word of the second stream) was fetched one cell ahead from its own 4-byte
+// stream, so the opacity gather starts together with the plan loads instead of after them.
+template <int S, bool PF>
+__device__ __forceinline__ void fetch_cell(Fetched<S>& f, const int4* __restrict__ plan, int ncells, int e, unsigned dword,
+                                           double md, double inv_m, const unsigned* __restrict__ wrap_tab, int side,
                                            const double* __restrict__ nhi)
 {
-    // plan cell: three coalesced 16-byte read-only loads (one per stream), shared by the S sources
-    const int4 r2 = __ldg(plan + 2 * (size_t)ncells + e);
-    const int4 r0 = __ldg(plan + e), r1 = __ldg(plan + (size_t)ncells + e);
-    f.wA = __hiloint2double(r0.y, r0.x);
-    f.wB = __hiloint2double(r0.w, r0.z);
-    f.path = __hiloint2double(r1.y, r1.x);
-    f.inv_np = __hiloint2double(r1.w, r1.z);
-    f.nb1 = r2.x & 0xffff;
-    f.nb2 = (unsigned)r2.x >> 16;
-    f.nb3 = r2.y & 0xffff;
-    f.nb4 = (unsigned)r2.y >> 16;
-    const unsigned di = r2.z & 0xff, dj = (r2.z >> 8) & 0xff, dk = (r2.z >> 16) & 0xff;
-    f.flags = ((unsigned)r2.z >> 24) & 0xffu;
+    if (PF) {
+        const unsigned di = dword & 0xff, dj = (dword >> 8) & 0xff, dk = (dword >> 16) & 0xff;
 #pragma unroll
-    for (int s = 0; s < S; s++) {
-        const unsigned* w = wrap_tab + 3 * s * side;
-        f.pos[s] = w[di] + w[side + dj] + w[2 * side + dk];  // N <= 1600: fits 32 bits
-        f.nhi[s] = __ldg(nhi + f.pos[s]);
+        for (int s = 0; s < S; s++) {
+            const unsigned* w = wrap_tab + 3 * s * side;
+            f.pos[s] = w[di] + w[side + dj] + w[2 * side + dk];
+            f.nhi[s] = __ldg(nhi + f.pos[s]);
+        }
+    }
+    const int4 rb = __ldg(plan + (size_t)ncells + e);
+    const int4 ra = __ldg(plan + e);
+    f.path = __hiloint2double(ra.y, ra.x);
+    f.inv_np = __hiloint2double(ra.w, ra.z);
+    f.nb1 = rb.x & 0xffff;
+    f.nb2 = (unsigned)rb.x >> 16;
+    f.nb3 = rb.y & 0xffff;
+    f.nb4 = (unsigned)rb.y >> 16;
+    f.flags = ((unsigned)rb.z >> 24) & 0xffu;
+    const double da = (double)(rb.w & 0xff), db = (double)((rb.w >> 8) & 0xff);
+    const double qa = da * inv_m, qb = db * inv_m;
+    f.wA = fma(fma(-md, qa, da), inv_m, qa);
+    f.wB = fma(fma(-md, qb, db), inv_m, qb);
+    if (!PF) {
+        const unsigned di = rb.z & 0xff, dj = (rb.z >> 8) & 0xff, dk = (rb.z >> 16) & 0xff;
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const unsigned* w = wrap_tab + 3 * s * side;
+            f.pos[s] = w[di] + w[side + dj] + w[2 * side + dk];  // N <= 1600: fits 32 bits
+            f.nhi[s] = __ldg(nhi + f.pos[s]);
+        }
     }
 }
 
-// One CTA per S sources.  Per level: every thread updates its cells (plan entry + neutral density from
-// global memory, four upstream column densities from the previous level's shared-memory buffer), then a
-// CTA barrier hands the level over.  Three latency-hiding variants were measured on B200 and dropped, all
-// because the kernel sits exactly at the 64-register limit that 32 resident warps allow: holding the whole
-// next cell (plan entry + neutral density) in registers across the barrier (30 % slower), fetching only the
-// 16-byte offsets stream one cell ahead (10-40 % slower, spills), and prefetch.global.L1 of the next plan
-// entry (4 % slower).
-template <int S, int BLOCK, int MINB>
+// One level of the sweep for the S sources of a CTA.
+template <int S, int BLOCK, int REP, bool DIAG, bool CDOUT, bool TEX, bool PF>
+__device__ __forceinline__ void sweep_level(const int4* __restrict__ plan, const unsigned* __restrict__ dwords, int ncells,
+                                            int beg, int end, int m, double* __restrict__ cur,
+                                            const double* __restrict__ prev, int max_level_cells,
+                                            const unsigned* __restrict__ wrap_tab, int side, const double (&sk)[S],
+                                            const bool (&live)[S], const SweepParams& p,
+                                            const double2* __restrict__ log2_tab)
+{
+    const double md = (double)m, inv_m = kInvLevel[m];
+    int e = beg + threadIdx.x;
+    unsigned dword = 0;
+    if (PF && e < end) dword = __ldg(dwords + e);
+    for (; e < end; e += BLOCK) {
+        unsigned dnext = 0;
+        if (PF && e + BLOCK < end) dnext = __ldg(dwords + e + BLOCK);
+        Fetched<S> c;
+        fetch_cell<S, PF>(c, plan, ncells, e, dword, md, inv_m, wrap_tab, side, p.nhi);
+        const int slot = e - beg;
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            if (!live[s]) continue;
+            const double* pv = prev + s * max_level_cells;
+            const double cin = interp_coldens<false, DIAG>(pv[c.nb1], pv[c.nb2], pv[c.nb3], pv[c.nb4], c.wA, c.wB, c.flags);
+            const double cdho = finish_cell<REP, TEX>(cin, c.path, c.inv_np, c.flags, c.nhi[s], sk[s], c.pos[s], p, log2_tab);
+            cur[s * max_level_cells + slot] = cdho;
+            if (CDOUT) p.coldens_out[c.pos[s]] = cdho;
+        }
+        dword = dnext;
+    }
+}
+
+// One CTA per S sources.  Per level every thread updates its cells (plan entry + opacity from global memory,
+// four upstream optical depths from the previous level's shared-memory buffer), then a CTA barrier hands
+// the level over.  Three latency-hiding variants were measured on B200 and dropped, all because the kernel
+// sits exactly at the 64-register limit that 32 resident warps allow: holding the whole next cell (plan entry
+// + opacity) in registers across the barrier (30 % slower), fetching only the 16-byte offsets stream one
+// cell ahead (10-40 % slower, spills), and prefetch.global.L1 of the next plan entry (4 % slower).
+template <int S, int BLOCK, int MINB, int REP, bool CDOUT, bool TEX, bool PF>
 __global__ void __launch_bounds__(BLOCK, MINB)
-sweep_smem_kernel(const int4* __restrict__ plan, int ncells, const int* __restrict__ level_start_all,
+sweep_smem_kernel(const int4* __restrict__ plan, const unsigned* __restrict__ dwords, int ncells,
+                  const int* __restrict__ level_start_all,
                                   int nlevels, int max_level_cells, int lo, int side, int parts, SweepParams p)
 {
     extern __shared__ double2 sh_raw[];
-    double2* log2_tab = sh_raw;                                 // 256 entries
-    double* sh_cd = reinterpret_cast<double*>(sh_raw + 256);    // [2][S][max_level_cells]
+    double2* log2_all = sh_raw;                                        // 256 entries x REP copies
+    double* sh_cd = reinterpret_cast<double*>(sh_raw + 256 * REP);     // [2][S][max_level_cells]
     unsigned* wrap_tab = reinterpret_cast<unsigned*>(sh_cd + (size_t)2 * S * max_level_cells);  // [S][3][side]
     const int N = p.N;
     // CTA -> (group of S sources, part of the sweep)
@@ -241,12 +351,13 @@ sweep_smem_kernel(const int4* __restrict__ plan, int ncells, const int* __restri
     const int first = (blockIdx.x / parts) * S;
     const int* __restrict__ level_start = level_start_all + part * (nlevels + 1);
 
-    for (int t = threadIdx.x; t < 256; t += BLOCK) log2_tab[t] = __ldg(p.log2_tab + t);
+    for (int t = threadIdx.x; t < 256 * REP; t += BLOCK) log2_all[t] = __ldg(p.log2_tab + t / REP);
+    const double2* log2_tab = log2_all + (REP > 1 ? (threadIdx.x & (REP - 1)) : 0);
     // the source cell "interpolates" slot 0 of the (empty) previous level with weight 1: seed it with 0
     if (threadIdx.x < S) sh_cd[(size_t)S * max_level_cells + threadIdx.x * max_level_cells] = 0.0;
 
     int i0[S], j0[S], k0[S];
-    double flux[S];
+    double sk[S];
     bool live[S];
 #pragma unroll
     for (int s = 0; s < S; s++) {
@@ -255,7 +366,7 @@ sweep_smem_kernel(const int4* __restrict__ plan, int ncells, const int* __restri
         i0[s] = p.src_pos[3 * ns + 0];
         j0[s] = p.src_pos[3 * ns + 1];
         k0[s] = p.src_pos[3 * ns + 2];
-        flux[s] = p.src_flux[ns];
+        sk[s] = p.src_flux[ns] * p.kpref;
     }
 #pragma unroll
     for (int s = 0; s < S; s++)
@@ -271,63 +382,66 @@ sweep_smem_kernel(const int4* __restrict__ plan, int ncells, const int* __restri
         const int beg = __ldg(level_start + m), end = __ldg(level_start + m + 1);
         double* cur = sh_cd + (size_t)(m & 1) * S * max_level_cells;
         const double* prev = sh_cd + (size_t)((m & 1) ^ 1) * S * max_level_cells;
-        for (int e = beg + threadIdx.x; e < end; e += BLOCK) {
-            Fetched<S> c;
-            fetch_cell<S>(c, plan, ncells, e, wrap_tab, side, p.nhi);
-            const int slot = e - beg;
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-                if (!live[s]) continue;
-                const double* pv = prev + s * max_level_cells;
-                const double cin = interp_coldens<false>(pv[c.nb1], pv[c.nb2], pv[c.nb3], pv[c.nb4], c.wA, c.wB, c.flags);
-                const double cdho = finish_cell(cin, c.path, c.inv_np, c.flags, c.nhi[s], flux[s], c.pos[s], p, log2_tab);
-                cur[s * max_level_cells + slot] = cdho;
-                if (p.coldens_out) p.coldens_out[c.pos[s]] = cdho;
-            }
-        }
+        if (m < 2)
+            sweep_level<S, BLOCK, REP, true, CDOUT, TEX, PF>(plan, dwords, ncells, beg, end, m, cur, prev, max_level_cells,
+                                                             wrap_tab, side, sk, live, p, log2_tab);
+        else
+            sweep_level<S, BLOCK, REP, false, CDOUT, TEX, PF>(plan, dwords, ncells, beg, end, m, cur, prev, max_level_cells,
+                                                              wrap_tab, side, sk, live, p, log2_tab);
         __syncthreads();
     }
 }
 
-size_t sweep_smem_bytes(const SweepPlan& plan, int S)
+size_t sweep_smem_bytes(const SweepPlan& plan, int S, int rep)
 {
-    return 256 * sizeof(double2) + (size_t)2 * S * plan.max_level_cells * sizeof(double) +
+    return (size_t)256 * rep * sizeof(double2) + (size_t)2 * S * plan.max_level_cells * sizeof(double) +
            (size_t)3 * S * plan.side * sizeof(unsigned);
 }
 
-template <int S, int BLOCK, int MINB>
+template <int S, int BLOCK, int MINB, int REP, bool CDOUT, bool TEX, bool PF>
 static cudaError_t launch_smem_t(const SweepPlan& plan, const SweepParams& p, cudaStream_t stream)
 {
-    const size_t smem = sweep_smem_bytes(plan, S);
-    cudaError_t e = cudaFuncSetAttribute(sweep_smem_kernel<S, BLOCK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    const size_t smem = sweep_smem_bytes(plan, S, REP);
     const int grid = ((p.src_count + S - 1) / S) * plan.parts;
-    sweep_smem_kernel<S, BLOCK, MINB><<<grid, BLOCK, smem, stream>>>(plan.d_cells, (int)plan.ncells, plan.d_level_start,
-                                                                   plan.nlevels, plan.max_level_cells, plan.lo,
-                                                                   plan.side, plan.parts, p);
+    auto kernel = sweep_smem_kernel<S, BLOCK, MINB, REP, CDOUT, TEX, PF>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, BLOCK, smem, stream>>>(plan.d_cells, plan.d_dwords, (int)plan.ncells, plan.d_level_start, plan.nlevels,
+                                          plan.max_level_cells, plan.lo, plan.side, plan.parts, p);
     return cudaGetLastError();
 }
 
-// `block` in {128,256,512,1024}; `regs_mode` 0 caps registers at 64/thread (full occupancy), 1 allows
-// ~128/thread (half occupancy, no spills of the prefetch registers).
-cudaError_t launch_sweep_smem(const SweepPlan& plan, const SweepParams& p, int S, int block, int regs_mode,
+template <int S, int BLOCK, int MINB>
+static cudaError_t launch_smem_opts(const SweepPlan& plan, const SweepParams& p, int opts, cudaStream_t stream)
+{
+    if (p.coldens_out) return launch_smem_t<S, BLOCK, MINB, 1, true, false, false>(plan, p, stream);  // debug path
+    switch (opts & 7) {
+        case 0: return launch_smem_t<S, BLOCK, MINB, 1, false, false, false>(plan, p, stream);
+        case 1: return launch_smem_t<S, BLOCK, MINB, 8, false, false, false>(plan, p, stream);
+        case 2: return launch_smem_t<S, BLOCK, MINB, 1, false, true, false>(plan, p, stream);
+        case 3: return launch_smem_t<S, BLOCK, MINB, 8, false, true, false>(plan, p, stream);
+        case 4: return launch_smem_t<S, BLOCK, MINB, 1, false, false, true>(plan, p, stream);
+        case 5: return launch_smem_t<S, BLOCK, MINB, 8, false, false, true>(plan, p, stream);
+        case 6: return launch_smem_t<S, BLOCK, MINB, 1, false, true, true>(plan, p, stream);
+        default: return launch_smem_t<S, BLOCK, MINB, 8, false, true, true>(plan, p, stream);
+    }
+}
+
+// `block` in {256,512,1024}; `opts`: bit 0 eight copies of the log2 table in shared memory, bit 1 table gathers
+// through the texture pipe, bit 2 offsets word fetched one cell ahead.
+cudaError_t launch_sweep_smem(const SweepPlan& plan, const SweepParams& p, int S, int block, int opts,
                               cudaStream_t stream, int* launches)
 {
     if (p.src_count <= 0) return cudaSuccess;
     if (launches) *launches += 1;
-#define ASORA_CASE(SS, BB, M0, M1)                                                       \
-    if (S == SS && block == BB)                                                          \
-        return regs_mode ? launch_smem_t<SS, BB, M1>(plan, p, stream) : launch_smem_t<SS, BB, M0>(plan, p, stream);
-    ASORA_CASE(1, 128, 8, 4)
-    ASORA_CASE(1, 256, 4, 2)
-    ASORA_CASE(1, 512, 2, 1)
-    ASORA_CASE(1, 1024, 1, 1)
-    ASORA_CASE(2, 128, 8, 4)
-    ASORA_CASE(2, 256, 4, 2)
-    ASORA_CASE(2, 512, 2, 1)
-    ASORA_CASE(2, 1024, 1, 1)
-    ASORA_CASE(4, 256, 4, 2)
-    ASORA_CASE(4, 512, 2, 1)
+#define ASORA_CASE(SS, BB, MB) \
+    if (S == SS && block == BB) return launch_smem_opts<SS, BB, MB>(plan, p, opts, stream);
+    ASORA_CASE(1, 256, 4)
+    ASORA_CASE(1, 512, 2)
+    ASORA_CASE(1, 1024, 1)
+    ASORA_CASE(2, 256, 4)
+    ASORA_CASE(2, 512, 2)
+    ASORA_CASE(2, 1024, 1)
 #undef ASORA_CASE
     return cudaErrorInvalidValue;
 }
@@ -406,7 +520,7 @@ sweep_grid_kernel(SweepParams p, int nlevels, int ngroups, int group_ctas, unsig
     for (int sidx = group; sidx < p.src_count; sidx += ngroups) {
         const int ns = p.src_begin + sidx;
         const int i0 = p.src_pos[3 * ns + 0], j0 = p.src_pos[3 * ns + 1], k0 = p.src_pos[3 * ns + 2];
-        const double strength = p.src_flux[ns];
+        const double sk = p.src_flux[ns] * p.kpref;
         for (int m = 0; m < nlevels; m++) {
             const long long ncell = (m == 0) ? 1 : 24LL * m * m + 2;
             for (long long t = tid; t < ncell; t += nthreads) {
@@ -462,9 +576,9 @@ sweep_grid_kernel(SweepParams p, int nlevels, int ngroups, int group_ctas, unsig
                     const double c2 = (wB * (1.0 - wA) != 0.0) ? __ldcg(slab + q2) : 0.0;
                     const double c3 = (wA * (1.0 - wB) != 0.0) ? __ldcg(slab + q3) : 0.0;
                     const double c4 = ((1.0 - wA) * (1.0 - wB) != 0.0) ? __ldcg(slab + q4) : 0.0;
-                    cin = interp_coldens<true>(c1, c2, c3, c4, wA, wB, flags);
+                    cin = interp_coldens<true, true>(c1, c2, c3, c4, wA, wB, flags);
                 }
-                const double cdho = finish_cell(cin, path, inv_np, flags, nHI_p, strength, pos, p, log2_tab);
+                const double cdho = finish_cell<1, false>(cin, path, inv_np, flags, nHI_p, sk, pos, p, log2_tab);
                 __stcg(slab + pos, cdho);
             }
             group_barrier(counter, (unsigned)group_ctas, epoch);
@@ -538,6 +652,29 @@ cudaError_t launch_prepare_nhi(const double* ndens, const double* xh_av, double*
     int64_t blocks = (ncell + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     prepare_nhi_kernel<<<(int)blocks, 256, 0, stream>>>(ndens, xh_av, ntau, sig_dr, ncell);
+    return cudaGetLastError();
+}
+
+// phi = sum / ntau: the division by the cell's own opacity that every (source, cell) rate shares
+// (raytracing.cu:324, finish_cell above).  A cell no source deposited into keeps 0 also where it is fully ionised
+// (the reference leaves 0 in unvisited cells and 0/0 in visited ones, SURVEY note N7).  `keep` (optional) holds
+// rates of earlier sweeps to add on top.
+__global__ void finish_phi_kernel(double* __restrict__ phi, const double* __restrict__ ntau,
+                                  const double* __restrict__ keep, int64_t ncell)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (int64_t)gridDim.x * blockDim.x) {
+        const double sum = phi[i];
+        double v = (sum != 0.0) ? sum / ntau[i] : 0.0;
+        if (keep) v += keep[i];
+        phi[i] = v;
+    }
+}
+
+cudaError_t launch_finish_phi(double* phi, const double* ntau, const double* keep, int64_t ncell, cudaStream_t stream)
+{
+    int64_t blocks = (ncell + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    finish_phi_kernel<<<(int)blocks, 256, 0, stream>>>(phi, ntau, keep, ncell);
     return cudaGetLastError();
 }
 

@@ -174,7 +174,7 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_o
                     pc.d[0] = (uint8_t)(i - lo);
                     pc.d[1] = (uint8_t)(j - lo);
                     pc.d[2] = (uint8_t)(k - lo);
-                    pc.pad = 0;
+                    pc.ab = 0;
                     pc.flags = 0;
                     pc.nb[0] = pc.nb[1] = pc.nb[2] = pc.nb[3] = 0;
                     if (m == 0) {
@@ -212,6 +212,7 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_o
                         }
                         // With dx = 1 - a/c (raytracing.cu:397-403 in source-relative coordinates) the
                         // bilinear weights are s1 = wA*wB, s2 = wB*(1-wA), s3 = wA*(1-wB), s4 = (1-wA)*(1-wB).
+                        pc.ab = (uint32_t)a | ((uint32_t)b << 8);
                         pc.wA = (double)a / (double)c;
                         pc.wB = (double)b / (double)c;
                         const double da = a, db = b, dc = c;
@@ -255,14 +256,18 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_o
     plan.parts = parts;
     plan.ncells = total;
 
-    std::vector<int4> soa(3 * (size_t)total);
+    std::vector<int4> soa(2 * (size_t)total);
     for (int64_t e = 0; e < total; e++) {
         const int4* src = reinterpret_cast<const int4*>(&plan.cells[e]);
-        soa[e] = src[0];
-        soa[total + e] = src[1];
-        soa[2 * total + e] = src[2];
+        soa[e] = src[1];
+        soa[total + e] = src[2];
     }
+    std::vector<unsigned> dwords((size_t)total);
+    for (int64_t e = 0; e < total; e++) dwords[e] = (unsigned)soa[total + e].z;
     cudaError_t e = cudaMalloc(&plan.d_cells, sizeof(int4) * soa.size());
+    if (e == cudaSuccess) e = cudaMalloc(&plan.d_dwords, sizeof(unsigned) * dwords.size());
+    if (e == cudaSuccess)
+        e = cudaMemcpy(plan.d_dwords, dwords.data(), sizeof(unsigned) * dwords.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&plan.d_level_start, sizeof(int) * plan.level_start.size());
     if (e == cudaSuccess)
         e = cudaMemcpy(plan.d_cells, soa.data(), sizeof(int4) * soa.size(), cudaMemcpyHostToDevice);
@@ -282,6 +287,8 @@ void free_sweep_plan(SweepPlan& plan)
 {
     if (plan.d_cells) cudaFree(plan.d_cells);
     if (plan.d_level_start) cudaFree(plan.d_level_start);
+    if (plan.d_dwords) cudaFree(plan.d_dwords);
+    plan.d_dwords = nullptr;
     plan.d_cells = nullptr;
     plan.d_level_start = nullptr;
     plan.cells.clear();
