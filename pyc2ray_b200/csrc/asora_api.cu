@@ -180,7 +180,9 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     p.lut_b = 0.30102999566398119521 / dlogtau;
     p.lut_a = 1.0 - minlogtau / dlogtau;
     // rates.cu:77-78 clamps: tau >= 1e-20, 0 <= index <= NumTau  <=>  tau_lo <= tau <= tau_hi
-    p.tau_lo = std::max(1.0e-20, std::pow(10.0, minlogtau - dlogtau));
+    // (a hair above the exact bound, 4e-10 of a table bin, so that rounding in the logarithm cannot produce a
+    // negative index: table_index takes floor() by a rounded-down addition, which assumes index >= 0)
+    p.tau_lo = std::max(1.0e-20, std::pow(10.0, minlogtau - dlogtau)) * (1.0 + 1e-12);
     p.tau_hi = std::pow(10.0, minlogtau + ((double)NumTau - 1.0) * dlogtau);
     {   // fast range test of photo_lookup: high words strictly between those of tau_lo and tau_hi
         uint64_t blo, bhi;
@@ -258,20 +260,20 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
                 // does; two sources per CTA (plan decode and barriers amortised) when both fit next to >= 3
                 // resident CTAs.
                 const int maxc = g.plan.max_level_cells;
-                block = maxc < 2048 ? 256 : (2 * per_src <= budget ? 512 : 1024);
+                // (one CTA per SM: 896 threads at 72 registers beat 1024 at 64, where ptxas spills and delays
+                // loads, and 768 / 640 / 512 threads: 17.7 vs 18.3 / 17.8 / 18.6 / 20.5 ms at R = 30)
+                block = maxc < 2048 ? 256 : (2 * per_src <= budget ? 512 : 896);
                 S = (block == 256 && count >= 8 * g.sm_count && 3 * sweep_smem_bytes(g.plan, 2, 1) <= budget) ? 2 : 1;
                 if (g.tune_S > 0 && (size_t)g.tune_S * per_src <= budget) S = g.tune_S;
                 if (g.tune_block > 0) block = g.tune_block;
-                // eight bank-staggered copies of the log2 table (28 KB more) when they do not cost a resident CTA
-                const int want = block >= 1024 ? 1 : (block == 512 ? 2 : 4);
-                const size_t per_sm = (size_t)g.smem_per_sm;
-                const size_t with8 = sweep_smem_bytes(g.plan, S, 8) + 1024;
-                opts = (with8 <= budget && want * with8 <= per_sm) ? 1 : 0;
+                // eight bank-staggered copies of the log2 table (28 KB more) for the long-lived one-per-SM CTAs of large
+                // radii; short sweeps do not recover the cost of filling them (R = 10.76: 1.20 vs 1.13 ms)
+                opts = (block > 512 && sweep_smem_bytes(g.plan, S, 8) <= budget) ? 1 : 0;
                 // table gathers through the texture pipe: always (R = 30: 18.9 -> 18.2 ms; R = 10.76: 1.25 -> 1.21 ms);
                 // offsets word one cell ahead: only the small-radius shape gains (R = 10.76, two sources x 256
                 // threads: 1.21 -> 1.11 ms; R = 30, 1024 threads: 18.2 -> 18.9 ms) -- scripts/perf_probe6.py
                 opts |= 2;
-                if (block == 256) opts |= 4;
+                if (block == 256 || block == 896) opts |= 4;
                 opts ^= g.tune_opts;  // profiling knob: bits 16-18 of set_tuning's block_threads toggle the options
             }
         }

@@ -53,6 +53,11 @@ cudaError_t upload_inv_levels()
 __constant__ double kLog2Poly[6] = {1.44269504088896341, -0.72134752044448170, 0.48089834696298783,
                                     -0.36067376022224085, 0.28853900817779268, -0.24044917348149391};
 
+// (double)u for 0 <= u < 2^31 without the conversion unit: I2F / F2I run on the 16-lane XU pipe (8 cycles per warp,
+// long latency; 9 of them per rated update kept that pipe 16 % busy), a DADD on the fp64 pipe takes 2.
+#define ASORA_TWO52 4503599627370496.0
+__device__ __forceinline__ double u2d(unsigned u) { return __hiloint2double(0x43300000, (int)u) - ASORA_TWO52; }
+
 // max / min for ordinary (non-NaN) operands: one DSETP and two FSELs.  fmax()/fmin() cost 6-8
 // instructions each on sm_100 because of their NaN rules.
 // (Written in PTX: nvcc pattern-matches the C++ ternary back into max.f64, which sm_100 emulates with a
@@ -78,7 +83,7 @@ __device__ __forceinline__ double dmin(double a, double b)
 template <int REP>
 __device__ __forceinline__ double fast_log2(int hi, int lo, const double2* __restrict__ tab)
 {
-    const int e = (hi >> 20) - 1023;
+    const double e = __hiloint2double(0x43300000, hi >> 20) - (ASORA_TWO52 + 1023.0);  // unbiased exponent, exact
     const double2 t = tab[((hi >> 12) & 0xff) * REP];
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
     const double r = fma(m, t.x, -1.0);  // |r| <= 2^-9
@@ -87,7 +92,7 @@ __device__ __forceinline__ double fast_log2(int hi, int lo, const double2* __res
     p = fma(r, p, kLog2Poly[2]);
     p = fma(r, p, kLog2Poly[1]);
     p = fma(r, p, kLog2Poly[0]);
-    return fma(r, p, (double)e + t.y);
+    return fma(r, p, e + t.y);
 }
 
 void host_log2_table(double* tab512)
@@ -124,9 +129,12 @@ template <int REP>
 __device__ __forceinline__ TableIndex table_index(int hi, int lo, const SweepParams& p, const double2* __restrict__ log2_tab)
 {
     const double real_i = fma(p.lut_b, fast_log2<REP>(hi, lo, log2_tab), p.lut_a);
+    // floor and fraction of 0 <= real_i < 2^31 (tau is clamped): adding 2^52 rounding down leaves floor(real_i) in
+    // the low word
+    const double shifted = __dadd_rd(real_i, ASORA_TWO52);
     TableIndex t;
-    t.i0 = (int)real_i;
-    t.residual = real_i - (double)t.i0;
+    t.i0 = __double2loint(shifted);
+    t.residual = real_i - (shifted - ASORA_TWO52);
     t.i0 = max(0, min(t.i0, p.ntab - 1));
     return t;
 }
@@ -282,7 +290,7 @@ __device__ __forceinline__ void fetch_cell(Fetched<S>& f, const int4* __restrict
     f.nb3 = rb.y & 0xffff;
     f.nb4 = (unsigned)rb.y >> 16;
     f.flags = ((unsigned)rb.z >> 24) & 0xffu;
-    const double da = (double)(rb.w & 0xff), db = (double)((rb.w >> 8) & 0xff);
+    const double da = u2d(rb.w & 0xff), db = u2d((rb.w >> 8) & 0xff);
     const double qa = da * inv_m, qb = db * inv_m;
     f.wA = fma(fma(-md, qa, da), inv_m, qa);
     f.wB = fma(fma(-md, qb, db), inv_m, qb);
@@ -346,10 +354,14 @@ sweep_smem_kernel(const int4* __restrict__ plan, const unsigned* __restrict__ dw
     double* sh_cd = reinterpret_cast<double*>(sh_raw + 256 * REP);     // [2][S][max_level_cells]
     unsigned* wrap_tab = reinterpret_cast<unsigned*>(sh_cd + (size_t)2 * S * max_level_cells);  // [S][3][side]
     const int N = p.N;
-    // CTA -> (group of S sources, part of the sweep)
-    const int part = blockIdx.x % parts;
-    const int first = (blockIdx.x / parts) * S;
-    const int* __restrict__ level_start = level_start_all + part * (nlevels + 1);
+    // CTA -> (part of the sweep, group of S sources), part-major: the parts of one source have identical work and
+    // would run in lock-step if they were co-resident; CTAs of different sources drift apart, so that one CTA's
+    // barrier waits and partially filled last passes overlap another CTA's arithmetic.
+    const int ngroups = gridDim.x / parts;
+    const int part = blockIdx.x / ngroups;
+    const int first = (blockIdx.x - part * ngroups) * S;
+    int* level_start = reinterpret_cast<int*>(wrap_tab + (size_t)3 * S * side);  // [nlevels + 1], shared memory
+    for (int t = threadIdx.x; t <= nlevels; t += BLOCK) level_start[t] = __ldg(level_start_all + part * (nlevels + 1) + t);
 
     for (int t = threadIdx.x; t < 256 * REP; t += BLOCK) log2_all[t] = __ldg(p.log2_tab + t / REP);
     const double2* log2_tab = log2_all + (REP > 1 ? (threadIdx.x & (REP - 1)) : 0);
@@ -378,8 +390,10 @@ sweep_smem_kernel(const int4* __restrict__ plan, const unsigned* __restrict__ dw
         }
     __syncthreads();
 
+    int beg = level_start[0], end = level_start[1];
     for (int m = 0; m < nlevels; m++) {
-        const int beg = __ldg(level_start + m), end = __ldg(level_start + m + 1);
+        // bounds of the next level, read before this level's work so that nothing but the barrier separates two levels
+        const int next_end = level_start[min(m + 2, nlevels)];
         double* cur = sh_cd + (size_t)(m & 1) * S * max_level_cells;
         const double* prev = sh_cd + (size_t)((m & 1) ^ 1) * S * max_level_cells;
         if (m < 2)
@@ -389,13 +403,15 @@ sweep_smem_kernel(const int4* __restrict__ plan, const unsigned* __restrict__ dw
             sweep_level<S, BLOCK, REP, false, CDOUT, TEX, PF>(plan, dwords, ncells, beg, end, m, cur, prev, max_level_cells,
                                                               wrap_tab, side, sk, live, p, log2_tab);
         __syncthreads();
+        beg = end;
+        end = next_end;
     }
 }
 
 size_t sweep_smem_bytes(const SweepPlan& plan, int S, int rep)
 {
     return (size_t)256 * rep * sizeof(double2) + (size_t)2 * S * plan.max_level_cells * sizeof(double) +
-           (size_t)3 * S * plan.side * sizeof(unsigned);
+           (size_t)3 * S * plan.side * sizeof(unsigned) + (size_t)(plan.nlevels + 1) * sizeof(int);
 }
 
 template <int S, int BLOCK, int MINB, int REP, bool CDOUT, bool TEX, bool PF>
@@ -439,7 +455,9 @@ cudaError_t launch_sweep_smem(const SweepPlan& plan, const SweepParams& p, int S
     ASORA_CASE(1, 256, 4)
     ASORA_CASE(1, 512, 2)
     ASORA_CASE(1, 1024, 1)
-    ASORA_CASE(2, 256, 4)
+    ASORA_CASE(2, 256, 3)  // 80 registers: at 64 the two-source body spills and its speed depends on where
+    ASORA_CASE(1, 768, 1)
+    ASORA_CASE(1, 896, 1)
     ASORA_CASE(2, 512, 2)
     ASORA_CASE(2, 1024, 1)
 #undef ASORA_CASE

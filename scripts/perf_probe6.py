@@ -17,7 +17,7 @@ nd, xh = f0_fields(N); pos_flat, flux_flat = p.format_sources(srcpos, flux)
 libasora.source_data_to_device(pos_flat, flux_flat, ns); libasora.density_to_device(np.ascontiguousarray(nd.ravel()), N)
 check(L.asora_buffer_upload(_cabi.BUF_XH_AV, _cabi.dptr(np.ascontiguousarray(xh.ravel()))))
 toggles = [int(a) for a in sys.argv[1:]] or list(range(8))
-for R, S, block in ((30.0, 1, 1024), (10.76, 2, 256)):
+for R, S, block in ((30.0, 0, 0), (10.76, 0, 0)):  # automatic launch shape, options toggled
     ref = None
     for t in toggles:
         check(L.asora_set_tuning(S, block | (t << 16))); best = 1e30
