@@ -62,6 +62,24 @@ int asora_source_data_to_device(const int32_t* pos, const double* flux, int NumS
 int asora_do_all_sources(double R, double sig, double dr, const double* xh_av, double* phi_ion,
                          int NumSrc, int N, double minlogtau, double dlogtau, int NumTau);
 
+/* ---- photo-heating rates --------------------------------------------------------------
+ * The reference computes phi_heat only in its CPU ray tracer (src/c2ray/photorates.f90:118,124,
+ * src/c2ray/raytracing.f90:530,537; f2py arguments heat_thin_table, heat_thick_table, phi_heat of
+ * libc2ray.raytracing.do_all_sources) and lists "add heating rate computation to ASORA" as a TODO
+ * (pyc2ray/c2ray_base.py:424-426).  These entry points are what that extension of libasora would bind. */
+
+/* Upload the heating tables (radiation/blackbody.py:79-85), same length as the photo tables already on the
+ * device.  photo_table_to_device discards them again. */
+int asora_heat_table_to_device(const double* heat_thin_table, const double* heat_thick_table, int NumTau);
+
+/* Heating on/off for the device-resident sweeps (asora_raytrace_device): when on, ASORA_BUF_PHI_HEAT receives
+ * the sum over sources of heat / nHI next to ASORA_BUF_PHI_ION. */
+int asora_set_heating(int on);
+
+/* asora_do_all_sources that also returns the photo-heating rates (host, N^3). */
+int asora_do_all_sources_heat(double R, double sig, double dr, const double* xh_av, double* phi_ion,
+                              double* phi_heat, int NumSrc, int N, double minlogtau, double dlogtau, int NumTau);
+
 /* ---- chemistry half of the boundary (f2py libc2ray.chemistry.global_pass) ------------------------ */
 
 /* replaces libc2ray.chemistry.global_pass(dt,ndens,temp,xh,xh_av,xh_intermed,phi_ion,bh00,albpow,
@@ -86,7 +104,8 @@ enum {
     ASORA_BUF_XH_INTERMED = 4, /* end-of-step ionised fraction of the current iteration */
     ASORA_BUF_TEMP = 5,
     ASORA_BUF_COLDENS = 6,     /* outgoing column density of the last debug sweep */
-    ASORA_BUF_COUNT = 7
+    ASORA_BUF_PHI_HEAT = 7,    /* photo-heating rates of the last sweep with heating on */
+    ASORA_BUF_COUNT = 8
 };
 
 /* Device address of a named buffer (allocated on first use), or NULL on error. */

@@ -57,6 +57,11 @@ def lib():
             ctypes.c_int, ctypes.c_int, dp, ip, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
             ctypes.c_double, dp, dp, dp, dp, dp, dp, ctypes.c_int, ctypes.c_double, ctypes.c_double,
             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int, dp]
+        L.oracle_do_all_sources_heat.restype = ctypes.c_long
+        L.oracle_do_all_sources_heat.argtypes = [
+            ctypes.c_int, ctypes.c_int, dp, ip, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+            ctypes.c_double, dp, dp, dp, dp, dp, dp, dp, dp, dp, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+            ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int, dp]
         L.oracle_global_pass.restype = ctypes.c_int
         L.oracle_global_pass.argtypes = [ctypes.c_double, dp, dp, dp, dp, dp, dp, ctypes.c_double,
                                          ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
@@ -79,6 +84,25 @@ def max_threads():
 def cells_per_source(N, R):
     """|octahedron(q_max) & cube| -- the per-source unit count of the updates/s metric."""
     return int(lib().oracle_cells_per_source(int(N), float(R)))
+
+
+def asora_do_all_sources_heat(R, sig, dr, ndens_flat, xh_av_flat, srcpos_flat, srcflux, N, thin, thick, heat_thin,
+                              heat_thick, minlogtau, dlogtau, NumTau, nthreads=1):
+    """asora_do_all_sources with photo-heating rates (photorates.f90:118,124 in the ASORA kernel's conventions).
+    Returns (phi_ion_flat, phi_heat_flat, n_updates)."""
+    n3 = N * N * N
+    nd = np.ascontiguousarray(ndens_flat, dtype=np.float64).ravel()
+    xa = np.ascontiguousarray(xh_av_flat, dtype=np.float64).ravel()
+    pos = np.ascontiguousarray(srcpos_flat, dtype=np.int32)
+    flux = np.ascontiguousarray(srcflux, dtype=np.float64)
+    tabs = [np.ascontiguousarray(t, dtype=np.float64) for t in (thin, thick, heat_thin, heat_thick)]
+    phi, heat, cdh, stats = np.zeros(n3), np.zeros(n3), np.zeros(n3), np.zeros(2)
+    n = lib().oracle_do_all_sources_heat(ASORA, OPT_FMA_DIST2, _dp(flux), pos.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                         flux.size, N, float(R), float(sig), float(dr), _dp(nd), _dp(xa), _dp(phi),
+                                         _dp(heat), _dp(cdh), _dp(tabs[0]), _dp(tabs[1]), _dp(tabs[2]), _dp(tabs[3]),
+                                         tabs[0].size, float(minlogtau), float(dlogtau), int(NumTau), 0, 0, 0.0,
+                                         int(nthreads), _dp(stats))
+    return phi, heat, int(n)
 
 
 def asora_do_all_sources(R, sig, dr, ndens_flat, xh_av_flat, srcpos_flat, srcflux, N, thin, thick,
@@ -110,7 +134,7 @@ def asora_do_all_sources(R, sig, dr, ndens_flat, xh_av_flat, srcpos_flat, srcflu
 
 def fortran_do_all_sources(normflux, srcpos, max_subbox, subboxsize, sig, dr, ndens, xh_av, loss_fraction,
                            thin, thick, minlogtau, dlogtau, R_max_LLS, NumTau=None, use_subbox=True,
-                           normflux_bug=False, nthreads=1):
+                           normflux_bug=False, nthreads=1, heat_thin=None, heat_thick=None):
     """CPU restatement of libc2ray.raytracing.do_all_sources (src/c2ray/raytracing.f90:52-119).
 
     srcpos is (3, NumSrc), 1-indexed; ndens / xh_av are (N,N,N) logical arrays (any memory order; they
@@ -130,6 +154,17 @@ def fortran_do_all_sources(normflux, srcpos, max_subbox, subboxsize, sig, dr, nd
     cdh = np.zeros((N, N, N), order="F")
     stats = np.zeros(2)
     opts = (OPT_USE_SUBBOX if use_subbox else 0) | (OPT_NORMFLUX_BUG if normflux_bug else 0)
+    if heat_thin is not None:
+        # with heating tables: returns phi_heat as a sixth value (raytracing.f90:52-110 fills it in place)
+        ht = np.ascontiguousarray(heat_thin, dtype=np.float64)
+        hk = np.ascontiguousarray(heat_thick, dtype=np.float64)
+        heat = np.zeros((N, N, N), order="F")
+        n = lib().oracle_do_all_sources_heat(FORTRAN, opts, _dp(flux), pos.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                             flux.size, N, float(R_max_LLS), float(sig), float(dr), _dp(nd), _dp(xa),
+                                             _dp(phi), _dp(heat), _dp(cdh), _dp(thin), _dp(thick), _dp(ht), _dp(hk),
+                                             thin.size, float(minlogtau), float(dlogtau), int(NumTau), int(max_subbox),
+                                             int(subboxsize), float(loss_fraction), int(nthreads), _dp(stats))
+        return phi, cdh, int(stats[0]), float(stats[1]), int(n), heat
     n = lib().oracle_do_all_sources(FORTRAN, opts, _dp(flux), pos.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
                                     flux.size, N, float(R_max_LLS), float(sig), float(dr), _dp(nd), _dp(xa),
                                     _dp(phi), _dp(cdh), _dp(thin), _dp(thick), thin.size, float(minlogtau),

@@ -104,7 +104,7 @@ static double photo_lookuptable(const double *table, double tau, double minlogta
     return table[i0] + residual * (table[i1] - table[i0]);
 }
 
-/* photorates.f90:62-127 == rates.cu:16-41 (photo-ionisation part; heating is not on the path) */
+/* photorates.f90:62-127 == rates.cu:16-41 (photo-ionisation part; heating: photoheat_rate below) */
 static double photoion_rates(const consts_t *c, double normflux, double coldens_in, double coldens_out,
                              double Vfact, double sig, const double *thin, const double *thick,
                              double minlogtau, double dlogtau, int NumTau, int ntab, double *phi_out)
@@ -124,6 +124,25 @@ static double photoion_rates(const consts_t *c, double normflux, double coldens_
         if (phi_out) *phi_out = phi_photo_in - cell;
     }
     return cell;
+}
+
+/* photorates.f90:118,124: photo-heating rate of a cell from the heating tables, with the same thick/thin
+ * split and table argument as the ionisation rate above (the ASORA flavour, which has no heating in the
+ * reference -- TODO at c2ray_base.py:424-426 --, keeps its own thin-cell argument tau_out, rates.cu:37). */
+static double photoheat_rate(const consts_t *c, double normflux, double coldens_in, double coldens_out, double Vfact,
+                             double sig, const double *heat_thin, const double *heat_thick, double minlogtau,
+                             double dlogtau, int NumTau, int ntab)
+{
+    double tau_in = coldens_in * sig;
+    double tau_out = coldens_out * sig;
+    double prefact = normflux / Vfact;
+    if (fabs(tau_out - tau_in) > c->tau_photo_limit)
+        return prefact * (photo_lookuptable(heat_thick, tau_in, minlogtau, dlogtau, NumTau, ntab) -
+                          photo_lookuptable(heat_thick, tau_out, minlogtau, dlogtau, NumTau, ntab));
+    {
+        double targ = c->thin_uses_tau_out ? tau_out : tau_in;
+        return prefact * (tau_out - tau_in) * photo_lookuptable(heat_thin, targ, minlogtau, dlogtau, NumTau, ntab);
+    }
 }
 
 /* raytracing.f90:807-813 == raytracing.cu:33 */
@@ -233,6 +252,8 @@ typedef struct {
     int N, fo, base, guard;
     double sig, dr, Rmax;
     const double *ndens, *xh_av, *thin, *thick;
+    const double *heat_thin, *heat_thick; /* NULL: no heating */
+    size_t heat_off;                      /* phi_heat of a cell lives heat_off doubles after its phi_ion */
     double minlogtau, dlogtau;
     int NumTau, ntab;
 } cellctx_t;
@@ -281,6 +302,11 @@ static int evolve0D(const cellctx_t *x, int i, int j, int k, int i0, int j0, int
             /* raytracing.cu:315-329 only touches phi_ion for rated cells; the Fortran adds 0/nHI
              * (raytracing.f90:519,531,536), which is the same unless nHI_p == 0 */
             phi_ion[pos] += phi;
+            if (x->heat_thick) { /* raytracing.f90:530,537 */
+                double heat = photoheat_rate(x->c, flux, coldensh_in, cdho, vol_ph, x->sig, x->heat_thin,
+                                             x->heat_thick, x->minlogtau, x->dlogtau, x->NumTau, x->ntab);
+                phi_ion[pos + x->heat_off] += heat / nHI_p;
+            }
         } else if (x->c->thin_uses_tau_out == 0) {
             phi_ion[pos] += 0.0 / nHI_p;
         }
@@ -420,14 +446,18 @@ static long fortran_source(const cellctx_t *x, int opts, const int *sp, double f
  * nthreads > 1 parallelises over sources with per-thread scratch (not part of the reference,
  * which is serial: raytracing.f90:177); the per-thread partial phi grids are summed in thread order.
  * ------------------------------------------------------------------------------------------- */
-long oracle_do_all_sources(int flavour, int opts, const double *srcflux, const int32_t *srcpos, int NumSrc,
-                           int N, double R, double sig, double dr, const double *ndens, const double *xh_av,
-                           double *phi_ion, double *coldensh_out, const double *thin, const double *thick,
-                           int ntab, double minlogtau, double dlogtau, int NumTau, int max_subbox,
-                           int subboxsize, float loss_fraction, int nthreads, double *stats)
+static long do_all_sources_impl(int flavour, int opts, const double *srcflux, const int32_t *srcpos, int NumSrc,
+                                int N, double R, double sig, double dr, const double *ndens, const double *xh_av,
+                                double *phi_out, double *coldensh_out, const double *thin, const double *thick,
+                                const double *heat_thin, const double *heat_thick, double *phi_heat_out,
+                                int ntab, double minlogtau, double dlogtau, int NumTau, int max_subbox,
+                                int subboxsize, float loss_fraction, int nthreads, double *stats)
 {
     const consts_t c = make_consts(flavour, opts);
     const size_t n3 = (size_t)N * N * N;
+    const int heating = (heat_thin && heat_thick && phi_heat_out);
+    const size_t nacc = heating ? 2 * n3 : n3; /* rates and, behind them, heating rates */
+    double *phi_ion = heating ? (double *)calloc(nacc, sizeof(double)) : phi_out;
     cellctx_t x;
     long total = 0;
     int sum_nbox = 0;
@@ -444,6 +474,9 @@ long oracle_do_all_sources(int flavour, int opts, const double *srcflux, const i
     x.xh_av = xh_av;
     x.thin = thin;
     x.thick = thick;
+    x.heat_thin = heating ? heat_thin : NULL;
+    x.heat_thick = heating ? heat_thick : NULL;
+    x.heat_off = n3;
     x.minlogtau = minlogtau;
     x.dlogtau = dlogtau;
     x.NumTau = NumTau;
@@ -451,7 +484,7 @@ long oracle_do_all_sources(int flavour, int opts, const double *srcflux, const i
     /* raytracing.cu:101 */
     const int q_max = (int)ceil(1.73205080757 * fmin(R, 1.73205080757 * N / 2.0));
 
-    memset(phi_ion, 0, sizeof(double) * n3);
+    memset(phi_ion, 0, sizeof(double) * nacc);
     if (nthreads < 1) nthreads = 1;
 #ifndef _OPENMP
     nthreads = 1;
@@ -477,7 +510,7 @@ long oracle_do_all_sources(int flavour, int opts, const double *srcflux, const i
         {
             int t = omp_get_thread_num();
             double *slab = (double *)calloc(n3, sizeof(double));
-            double *phi = (double *)calloc(n3, sizeof(double));
+            double *phi = (double *)calloc(nacc, sizeof(double));
             phis[t] = phi;
 #pragma omp for schedule(dynamic, 1)
             for (int ns = 0; ns < NumSrc; ns++) {
@@ -495,7 +528,7 @@ long oracle_do_all_sources(int flavour, int opts, const double *srcflux, const i
         }
         for (int t = 0; t < nthreads; t++) {
             if (!phis[t]) continue;
-            for (size_t p = 0; p < n3; p++) phi_ion[p] += phis[t][p];
+            for (size_t p = 0; p < nacc; p++) phi_ion[p] += phis[t][p];
             free(phis[t]);
         }
         free(phis);
@@ -505,7 +538,37 @@ long oracle_do_all_sources(int flavour, int opts, const double *srcflux, const i
         stats[0] = (double)sum_nbox;
         stats[1] = photon_loss;
     }
+    if (heating) {
+        memcpy(phi_out, phi_ion, sizeof(double) * n3);
+        memcpy(phi_heat_out, phi_ion + n3, sizeof(double) * n3);
+        free(phi_ion);
+    }
     return total;
+}
+
+long oracle_do_all_sources(int flavour, int opts, const double *srcflux, const int32_t *srcpos, int NumSrc,
+                           int N, double R, double sig, double dr, const double *ndens, const double *xh_av,
+                           double *phi_ion, double *coldensh_out, const double *thin, const double *thick,
+                           int ntab, double minlogtau, double dlogtau, int NumTau, int max_subbox,
+                           int subboxsize, float loss_fraction, int nthreads, double *stats)
+{
+    return do_all_sources_impl(flavour, opts, srcflux, srcpos, NumSrc, N, R, sig, dr, ndens, xh_av, phi_ion,
+                               coldensh_out, thin, thick, NULL, NULL, NULL, ntab, minlogtau, dlogtau, NumTau,
+                               max_subbox, subboxsize, loss_fraction, nthreads, stats);
+}
+
+/* The same with photo-heating rates (raytracing.f90:52-110 takes the heating tables and phi_heat): phi_heat
+ * receives sum over sources of heat / nHI (raytracing.f90:530,537). */
+long oracle_do_all_sources_heat(int flavour, int opts, const double *srcflux, const int32_t *srcpos, int NumSrc,
+                                int N, double R, double sig, double dr, const double *ndens, const double *xh_av,
+                                double *phi_ion, double *phi_heat, double *coldensh_out, const double *thin,
+                                const double *thick, const double *heat_thin, const double *heat_thick, int ntab,
+                                double minlogtau, double dlogtau, int NumTau, int max_subbox, int subboxsize,
+                                float loss_fraction, int nthreads, double *stats)
+{
+    return do_all_sources_impl(flavour, opts, srcflux, srcpos, NumSrc, N, R, sig, dr, ndens, xh_av, phi_ion,
+                               coldensh_out, thin, thick, heat_thin, heat_thick, phi_heat, ntab, minlogtau, dlogtau,
+                               NumTau, max_subbox, subboxsize, loss_fraction, nthreads, stats);
 }
 
 /* ---------------------------------------------------------------------------------------------

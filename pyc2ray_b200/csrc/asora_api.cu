@@ -32,6 +32,8 @@ struct Context {
     double2* thick = nullptr;
     cudaTextureObject_t tex_pairs = 0;  // one allocation: thick pairs, then thin pairs
     int ntab = 0;
+    bool heat_tables = false;  // heating half of the pair tables uploaded (asora_heat_table_to_device)
+    bool heating = false;      // accumulate ASORA_BUF_PHI_HEAT in the next sweeps (asora_set_heating)
     double* grid_scratch = nullptr;  // ngroups x N^3 column densities of the grid-cooperative sweep
     int grid_scratch_groups = 0;
     int grid_max_groups = 0;
@@ -98,8 +100,10 @@ void free_tables()
 {
     if (g.tex_pairs) cudaDestroyTextureObject(g.tex_pairs);
     g.tex_pairs = 0;
-    if (g.thick) cudaFree(g.thick);  // one allocation holds both tables
+    if (g.thick) cudaFree(g.thick);  // one allocation holds all four tables
     g.thin = g.thick = nullptr;
+    g.heat_tables = false;
+    g.heating = false;
 }
 
 int need_init()
@@ -199,6 +203,14 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     p.nhi = g.nhi;
     p.log2_tab = g.log2_tab;
     p.phi_ion = g.buf[ASORA_BUF_PHI_ION];
+    p.phi_heat = nullptr;
+    if (g.heating) {
+        if (!g.heat_tables) return fail("heating requested but no heating tables on device: call heat_table_to_device first");
+        if (coldens_grid) return fail("heating is not available on the single-source debug path");
+        if (!zero_phi) return fail("heating needs zero_phi = 1");
+        if (int rc = ensure_buffer(ASORA_BUF_PHI_HEAT)) return rc;
+        p.phi_heat = g.buf[ASORA_BUF_PHI_HEAT];
+    }
     p.thin = g.thin;
     p.thick = g.thick;
     p.tex_pairs = g.tex_pairs;
@@ -333,6 +345,7 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
                                    sizeof(double) * seg_len[sg], cudaMemcpyDeviceToDevice, g.stream));
             }
             CK(cudaMemsetAsync(g.buf[ASORA_BUF_PHI_ION] + seg_off[sg], 0, sizeof(double) * seg_len[sg], g.stream));
+            if (p.phi_heat) CK(cudaMemsetAsync(p.phi_heat + seg_off[sg], 0, sizeof(double) * seg_len[sg], g.stream));
         }
     }
 
@@ -358,6 +371,10 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
             if (seg_len[sg] <= 0) continue;
             cudaError_t e = launch_finish_phi(g.buf[ASORA_BUF_PHI_ION] + seg_off[sg], g.nhi + seg_off[sg],
                                               zero_phi ? nullptr : g.phi_keep + seg_off[sg], seg_len[sg], g.stream);
+            if (e == cudaSuccess && p.phi_heat) {  // raytracing.f90:530: the heating rate is divided by nHI as well
+                e = launch_finish_phi(p.phi_heat + seg_off[sg], g.nhi + seg_off[sg], nullptr, seg_len[sg], g.stream);
+                g.last_launches += 1;
+            }
             if (e != cudaSuccess) return fail_cuda("finish_phi_kernel launch", e);
             g.last_launches += 1;
         }
@@ -486,8 +503,10 @@ int asora_photo_table_to_device(const double* thin_table, const double* thick_ta
     free_tables();
     double* raw = nullptr;
     CK(cudaMalloc(&raw, sizeof(double) * 2 * (size_t)NumTau));
-    CK(cudaMalloc(&g.thick, sizeof(double2) * 2 * (size_t)NumTau));
+    CK(cudaMalloc(&g.thick, sizeof(double2) * 4 * (size_t)NumTau));  // thick, thin, heat thick, heat thin
+    CK(cudaMemsetAsync(g.thick, 0, sizeof(double2) * 4 * (size_t)NumTau, g.stream));
     g.thin = g.thick + NumTau;
+    g.heat_tables = false;
     CK(cudaMemcpyAsync(raw, thin_table, sizeof(double) * NumTau, cudaMemcpyHostToDevice, g.stream));
     CK(cudaMemcpyAsync(raw + NumTau, thick_table, sizeof(double) * NumTau, cudaMemcpyHostToDevice, g.stream));
     cudaError_t e = launch_pair_table(raw, g.thin, NumTau, g.stream);
@@ -502,12 +521,59 @@ int asora_photo_table_to_device(const double* thin_table, const double* thick_ta
         rd.resType = cudaResourceTypeLinear;
         rd.res.linear.devPtr = (void*)g.thick;
         rd.res.linear.desc = cudaCreateChannelDesc<int4>();
-        rd.res.linear.sizeInBytes = sizeof(double2) * 2 * (size_t)NumTau;
+        rd.res.linear.sizeInBytes = sizeof(double2) * 4 * (size_t)NumTau;
         cudaTextureDesc td;
         std::memset(&td, 0, sizeof(td));
         td.readMode = cudaReadModeElementType;
         CK(cudaCreateTextureObject(&g.tex_pairs, &rd, &td, nullptr));
     }
+    return 0;
+}
+
+int asora_heat_table_to_device(const double* heat_thin_table, const double* heat_thick_table, int NumTau)
+{
+    if (int rc = need_init()) return rc;
+    if (!g.thick) return fail("heat_table_to_device: call photo_table_to_device first");
+    if (NumTau != g.ntab || !heat_thin_table || !heat_thick_table)
+        return fail("heat_table_to_device: the heating tables must have the length of the photo tables");
+    double* raw = nullptr;
+    CK(cudaMalloc(&raw, sizeof(double) * 2 * (size_t)NumTau));
+    CK(cudaMemcpyAsync(raw, heat_thin_table, sizeof(double) * NumTau, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(raw + NumTau, heat_thick_table, sizeof(double) * NumTau, cudaMemcpyHostToDevice, g.stream));
+    cudaError_t e = launch_pair_table(raw + NumTau, g.thick + 2 * (size_t)NumTau, NumTau, g.stream);
+    if (e == cudaSuccess) e = launch_pair_table(raw, g.thick + 3 * (size_t)NumTau, NumTau, g.stream);
+    if (e != cudaSuccess) return fail_cuda("pair_table_kernel launch", e);
+    CK(cudaStreamSynchronize(g.stream));
+    cudaFree(raw);
+    g.heat_tables = true;
+    return 0;
+}
+
+int asora_set_heating(int on)
+{
+    if (int rc = need_init()) return rc;
+    if (on && !g.heat_tables) return fail("set_heating: no heating tables on device (heat_table_to_device)");
+    g.heating = on != 0;
+    return 0;
+}
+
+int asora_do_all_sources_heat(double R, double sig, double dr, const double* xh_av, double* phi_ion, double* phi_heat,
+                              int NumSrc, int N, double minlogtau, double dlogtau, int NumTau)
+{
+    if (int rc = need_init()) return rc;
+    if (N != g.N) return fail("do_all_sources_heat: m1 differs from device_init");
+    if (!xh_av || !phi_ion || !phi_heat) return fail("do_all_sources_heat: null pointer");
+    if (!g.heat_tables) return fail("do_all_sources_heat: no heating tables on device (heat_table_to_device)");
+    const bool was = g.heating;
+    g.heating = true;
+    CK(cudaMemcpyAsync(g.buf[ASORA_BUF_XH_AV], xh_av, sizeof(double) * g.ncell, cudaMemcpyHostToDevice, g.stream));
+    const int rc = run_sweep(R, sig, dr, 0, NumSrc, minlogtau, dlogtau, NumTau, true, nullptr);
+    g.heating = was;
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(phi_ion, g.buf[ASORA_BUF_PHI_ION], sizeof(double) * g.ncell, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaMemcpyAsync(phi_heat, g.buf[ASORA_BUF_PHI_HEAT], sizeof(double) * g.ncell, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1);
     return 0;
 }
 

@@ -82,9 +82,10 @@ struct SweepParams {
     int ntab;                 // uploaded table length
     const double* nhi;        // ntau = ndens * (1 - xh_av) * sigma * dr, refreshed before every sweep
     double* phi_ion;
-    const double2* thin;      // {T[i], T[i+1]-T[i]} pairs of the uploaded tables
-    const double2* thick;
-    cudaTextureObject_t tex_pairs;  // both pair tables as int4 texels: thick at [0, ntab), thin at [ntab, 2 ntab)
+    double* phi_heat;         // photo-heating rates, or null (heating off)
+    const double2* thick;     // {T[i], T[i+1]-T[i]} pairs of the uploaded tables, one allocation of 4 x ntab entries:
+    const double2* thin;      // thick, thin, heat thick, heat thin (the heating half is zero until uploaded)
+    cudaTextureObject_t tex_pairs;  // both pair tables as int4 texels: the same 4 x ntab entries
     const double2* log2_tab;  // 256 x {1/c_j, log2 c_j}, c_j the centre of mantissa bin j
     const int* src_pos;
     const double* src_flux;

@@ -143,9 +143,13 @@ __device__ __forceinline__ TableIndex table_index(int hi, int lo, const SweepPar
 // branch so that their logarithms and table loads overlap.
 // TEX: the two 16-byte gathers go through the texture pipe (tex1Dfetch) instead of LDG: a warp's 32 scattered
 // table pairs cost ~20 wavefronts on the LSU data pipe, the busiest unit of the sweep.
-template <int REP, bool TEX>
+// HEAT: the photo-heating tables (photorates.f90:118,124) share the index and the fraction of the ionisation
+// tables, so heating costs two more gathers and no logarithm.  All four pair tables live in one allocation /
+// one texture: thick, thin, heat thick, heat thin, ntab entries each.
+template <int REP, bool TEX, bool HEAT>
 __device__ __forceinline__ void photo_lookup2(bool thick, double tau_in, double tau_out, const SweepParams& p,
-                                              const double2* __restrict__ log2_tab, double& t_in, double& t_out)
+                                              const double2* __restrict__ log2_tab, double& t_in, double& t_out,
+                                              double& h_in, double& h_out)
 {
     int h1 = __double2hiint(tau_in), h2 = __double2hiint(tau_out);
     if (__builtin_expect(((unsigned)(h1 - p.hi_min) >= p.hi_span) | ((unsigned)(h2 - p.hi_min) >= p.hi_span), 0)) {
@@ -156,17 +160,29 @@ __device__ __forceinline__ void photo_lookup2(bool thick, double tau_in, double 
     }
     const TableIndex a = table_index<REP>(h1, __double2loint(tau_in), p, log2_tab);
     const TableIndex b = table_index<REP>(h2, __double2loint(tau_out), p, log2_tab);
+    const int ib = b.i0 + (thick ? 0 : p.ntab);  // thin table right behind the thick one
     if (TEX) {
-        // one texture over both tables (thick first): a per-lane choice of texture handle would need branches
         const int4 ua = tex1Dfetch<int4>(p.tex_pairs, a.i0);
-        const int4 ub = tex1Dfetch<int4>(p.tex_pairs, b.i0 + (thick ? 0 : p.ntab));
+        const int4 ub = tex1Dfetch<int4>(p.tex_pairs, ib);
         t_in = fma(a.residual, __hiloint2double(ua.w, ua.z), __hiloint2double(ua.y, ua.x));
         t_out = fma(b.residual, __hiloint2double(ub.w, ub.z), __hiloint2double(ub.y, ub.x));
+        if (HEAT) {
+            const int4 va = tex1Dfetch<int4>(p.tex_pairs, a.i0 + 2 * p.ntab);
+            const int4 vb = tex1Dfetch<int4>(p.tex_pairs, ib + 2 * p.ntab);
+            h_in = fma(a.residual, __hiloint2double(va.w, va.z), __hiloint2double(va.y, va.x));
+            h_out = fma(b.residual, __hiloint2double(vb.w, vb.z), __hiloint2double(vb.y, vb.x));
+        }
     } else {
         const double2 ta = __ldg(p.thick + a.i0);
-        const double2 tb = __ldg((thick ? p.thick : p.thin) + b.i0);
+        const double2 tb = __ldg(p.thick + ib);
         t_in = fma(a.residual, ta.y, ta.x);
         t_out = fma(b.residual, tb.y, tb.x);
+        if (HEAT) {
+            const double2 va = __ldg(p.thick + a.i0 + 2 * p.ntab);
+            const double2 vb = __ldg(p.thick + ib + 2 * p.ntab);
+            h_in = fma(a.residual, va.y, va.x);
+            h_out = fma(b.residual, vb.y, vb.x);
+        }
     }
 }
 
@@ -225,7 +241,7 @@ __device__ __forceinline__ int wrap(int i, int N)
 // The division by ntau is the same for every source that reaches the cell, so the sweep accumulates
 // strength * kpref * inv_np * absorbed and one pass over the grid divides afterwards (finish_phi_kernel):
 // sk = strength * kpref.  Returns the outgoing optical depth.
-template <int REP, bool TEX>
+template <int REP, bool TEX, bool HEAT>
 __device__ __forceinline__ double finish_cell(double tau_in, double path_cells, double inv_np, unsigned flags,
                                               double ntau_p, double sk, size_t pos, const SweepParams& p,
                                               const double2* __restrict__ log2_tab)
@@ -234,12 +250,16 @@ __device__ __forceinline__ double finish_cell(double tau_in, double path_cells, 
     if ((flags & PC_RATED) && tau_in <= p.tau_max) {  // coldensh_in <= MAX_COLDENSH (raytracing.cu:315)
         const double dtau = tau_out - tau_in;
         const bool thick = fabs(dtau) > ASORA_TAU_PHOTO_LIMIT;
-        double t_in, t_out;
-        photo_lookup2<REP, TEX>(thick, tau_in, tau_out, p, log2_tab, t_in, t_out);
+        double t_in, t_out, h_in = 0.0, h_out = 0.0;
+        photo_lookup2<REP, TEX, HEAT>(thick, tau_in, tau_out, p, log2_tab, t_in, t_out, h_in, h_out);
         // rates.cu:28-38: thick cells absorb T(tau_in) - T(tau_out), thin cells dtau * T_thin(tau_out)
         const double absorbed = thick ? (t_in - t_out) : dtau * t_out;
         // one fire-and-forget fp64 reduction per rated (source, cell) pair: RED.E.ADD.F64 at L2
         atomicAdd(p.phi_ion + pos, (sk * inv_np) * absorbed);
+        if (HEAT) {  // photorates.f90:118,124 + raytracing.f90:530,537, same prefactor and the same deferred / nHI
+            const double heated = thick ? (h_in - h_out) : dtau * h_out;
+            atomicAdd(p.phi_heat + pos, (sk * inv_np) * heated);
+        }
     }
     return tau_out;
 }
@@ -306,7 +326,7 @@ __device__ __forceinline__ void fetch_cell(Fetched<S>& f, const int4* __restrict
 }
 
 // One level of the sweep for the S sources of a CTA.
-template <int S, int BLOCK, int REP, bool DIAG, bool CDOUT, bool TEX, bool PF>
+template <int S, int BLOCK, int REP, bool DIAG, bool CDOUT, bool TEX, bool PF, bool HEAT>
 __device__ __forceinline__ void sweep_level(const int4* __restrict__ plan, const unsigned* __restrict__ dwords, int ncells,
                                             int beg, int end, int m, double* __restrict__ cur,
                                             const double* __restrict__ prev, int max_level_cells,
@@ -329,7 +349,7 @@ __device__ __forceinline__ void sweep_level(const int4* __restrict__ plan, const
             if (!live[s]) continue;
             const double* pv = prev + s * max_level_cells;
             const double cin = interp_coldens<false, DIAG>(pv[c.nb1], pv[c.nb2], pv[c.nb3], pv[c.nb4], c.wA, c.wB, c.flags);
-            const double cdho = finish_cell<REP, TEX>(cin, c.path, c.inv_np, c.flags, c.nhi[s], sk[s], c.pos[s], p, log2_tab);
+            const double cdho = finish_cell<REP, TEX, HEAT>(cin, c.path, c.inv_np, c.flags, c.nhi[s], sk[s], c.pos[s], p, log2_tab);
             cur[s * max_level_cells + slot] = cdho;
             if (CDOUT) p.coldens_out[c.pos[s]] = cdho;
         }
@@ -343,7 +363,7 @@ __device__ __forceinline__ void sweep_level(const int4* __restrict__ plan, const
 // sits exactly at the 64-register limit that 32 resident warps allow: holding the whole next cell (plan entry
 // + opacity) in registers across the barrier (30 % slower), fetching only the 16-byte offsets stream one
 // cell ahead (10-40 % slower, spills), and prefetch.global.L1 of the next plan entry (4 % slower).
-template <int S, int BLOCK, int MINB, int REP, bool CDOUT, bool TEX, bool PF>
+template <int S, int BLOCK, int MINB, int REP, bool CDOUT, bool TEX, bool PF, bool HEAT>
 __global__ void __launch_bounds__(BLOCK, MINB)
 sweep_smem_kernel(const int4* __restrict__ plan, const unsigned* __restrict__ dwords, int ncells,
                   const int* __restrict__ level_start_all,
@@ -397,10 +417,10 @@ sweep_smem_kernel(const int4* __restrict__ plan, const unsigned* __restrict__ dw
         double* cur = sh_cd + (size_t)(m & 1) * S * max_level_cells;
         const double* prev = sh_cd + (size_t)((m & 1) ^ 1) * S * max_level_cells;
         if (m < 2)
-            sweep_level<S, BLOCK, REP, true, CDOUT, TEX, PF>(plan, dwords, ncells, beg, end, m, cur, prev, max_level_cells,
+            sweep_level<S, BLOCK, REP, true, CDOUT, TEX, PF, HEAT>(plan, dwords, ncells, beg, end, m, cur, prev, max_level_cells,
                                                              wrap_tab, side, sk, live, p, log2_tab);
         else
-            sweep_level<S, BLOCK, REP, false, CDOUT, TEX, PF>(plan, dwords, ncells, beg, end, m, cur, prev, max_level_cells,
+            sweep_level<S, BLOCK, REP, false, CDOUT, TEX, PF, HEAT>(plan, dwords, ncells, beg, end, m, cur, prev, max_level_cells,
                                                               wrap_tab, side, sk, live, p, log2_tab);
         __syncthreads();
         beg = end;
@@ -414,12 +434,12 @@ size_t sweep_smem_bytes(const SweepPlan& plan, int S, int rep)
            (size_t)3 * S * plan.side * sizeof(unsigned) + (size_t)(plan.nlevels + 1) * sizeof(int);
 }
 
-template <int S, int BLOCK, int MINB, int REP, bool CDOUT, bool TEX, bool PF>
+template <int S, int BLOCK, int MINB, int REP, bool CDOUT, bool TEX, bool PF, bool HEAT = false>
 static cudaError_t launch_smem_t(const SweepPlan& plan, const SweepParams& p, cudaStream_t stream)
 {
     const size_t smem = sweep_smem_bytes(plan, S, REP);
     const int grid = ((p.src_count + S - 1) / S) * plan.parts;
-    auto kernel = sweep_smem_kernel<S, BLOCK, MINB, REP, CDOUT, TEX, PF>;
+    auto kernel = sweep_smem_kernel<S, BLOCK, MINB, REP, CDOUT, TEX, PF, HEAT>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kernel<<<grid, BLOCK, smem, stream>>>(plan.d_cells, plan.d_dwords, (int)plan.ncells, plan.d_level_start, plan.nlevels,
@@ -431,6 +451,7 @@ template <int S, int BLOCK, int MINB>
 static cudaError_t launch_smem_opts(const SweepPlan& plan, const SweepParams& p, int opts, cudaStream_t stream)
 {
     if (p.coldens_out) return launch_smem_t<S, BLOCK, MINB, 1, true, false, false>(plan, p, stream);  // debug path
+    if (p.phi_heat) return launch_smem_t<S, BLOCK, MINB, 1, false, true, false, true>(plan, p, stream);  // with heating
     switch (opts & 7) {
         case 0: return launch_smem_t<S, BLOCK, MINB, 1, false, false, false>(plan, p, stream);
         case 1: return launch_smem_t<S, BLOCK, MINB, 8, false, false, false>(plan, p, stream);
@@ -520,6 +541,7 @@ __device__ __forceinline__ void group_barrier(unsigned* counter, unsigned nctas,
 // The grid is split into `ngroups` groups of `group_ctas` CTAs; group g sweeps sources g, g+ngroups, ...
 // through its own N^3 scratch grid, so that sources whose levels are much narrower than the GPU run
 // side by side.  ngroups == 1 is "the whole GPU per source".
+template <bool HEAT>
 __global__ void __launch_bounds__(512, 2)
 sweep_grid_kernel(SweepParams p, int nlevels, int ngroups, int group_ctas, unsigned* counters)
 {
@@ -596,7 +618,7 @@ sweep_grid_kernel(SweepParams p, int nlevels, int ngroups, int group_ctas, unsig
                     const double c4 = ((1.0 - wA) * (1.0 - wB) != 0.0) ? __ldcg(slab + q4) : 0.0;
                     cin = interp_coldens<true, true>(c1, c2, c3, c4, wA, wB, flags);
                 }
-                const double cdho = finish_cell<1, false>(cin, path, inv_np, flags, nHI_p, sk, pos, p, log2_tab);
+                const double cdho = finish_cell<1, false, HEAT>(cin, path, inv_np, flags, nHI_p, sk, pos, p, log2_tab);
                 __stcg(slab + pos, cdho);
             }
             group_barrier(counter, (unsigned)group_ctas, epoch);
@@ -613,7 +635,7 @@ int sweep_grid_groups(const SweepParams& p, int max_groups, int* total_ctas_out,
         int dev = 0, sms = 0, per_sm = 0;
         if (cudaGetDevice(&dev) != cudaSuccess) return 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_grid_kernel, block, 0) != cudaSuccess) return 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_grid_kernel<true>, block, 0) != cudaSuccess) return 0;
         if (per_sm < 1) return 0;
         total_cached = sms * per_sm;
     }
@@ -647,7 +669,8 @@ cudaError_t launch_sweep_grid(const SweepParams& p, int ngroups, unsigned* count
     SweepParams pc = p;
     void* args[] = {(void*)&pc, (void*)&nlevels, (void*)&ngroups, (void*)&group_ctas, (void*)&counters};
     if (launches) *launches += 1;
-    return cudaLaunchCooperativeKernel((void*)sweep_grid_kernel, dim3(total), dim3(block), args, 0, stream);
+    void* kernel = pc.phi_heat ? (void*)sweep_grid_kernel<true> : (void*)sweep_grid_kernel<false>;
+    return cudaLaunchCooperativeKernel(kernel, dim3(total), dim3(block), args, 0, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------

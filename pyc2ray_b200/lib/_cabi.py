@@ -25,6 +25,9 @@ SIGNATURES = {
     "asora_photo_table_to_device": (_i, [c_dp, c_dp, _i]),
     "asora_source_data_to_device": (_i, [c_ip, c_dp, _i]),
     "asora_do_all_sources": (_i, [_d, _d, _d, c_dp, c_dp, _i, _i, _d, _d, _i]),
+    "asora_heat_table_to_device": (_i, [c_dp, c_dp, _i]),
+    "asora_set_heating": (_i, [_i]),
+    "asora_do_all_sources_heat": (_i, [_d, _d, _d, c_dp, c_dp, c_dp, _i, _i, _d, _d, _i]),
     "asora_global_pass": (_i, [_d, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, _d, _d, _d, _d, _d, _i64,
                                ctypes.POINTER(_i)]),
     "asora_device_buffer": (ctypes.c_void_p, [_i]),
@@ -55,7 +58,7 @@ for _name, (_res, _args) in SIGNATURES.items():
     _f.restype = _res
     _f.argtypes = _args
 
-BUF_NDENS, BUF_XH_AV, BUF_PHI_ION, BUF_XH, BUF_XH_INTERMED, BUF_TEMP, BUF_COLDENS = range(7)
+BUF_NDENS, BUF_XH_AV, BUF_PHI_ION, BUF_XH, BUF_XH_INTERMED, BUF_TEMP, BUF_COLDENS, BUF_PHI_HEAT = range(8)
 
 
 def check(rc):

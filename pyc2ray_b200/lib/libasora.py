@@ -12,7 +12,7 @@ from . import _cabi
 from ._cabi import L, check, dptr, iptr
 
 __all__ = ["do_all_sources", "device_init", "device_close", "density_to_device", "photo_table_to_device",
-           "source_data_to_device"]
+           "source_data_to_device", "heat_table_to_device", "do_all_sources_heat"]
 
 _N = None
 
@@ -76,3 +76,29 @@ def do_all_sources(R, coldensh_out, sig, dr, ndens, xh_av, phi_ion, NumSrc, m1, 
         raise ValueError("phi_ion must be writeable")
     check(L.asora_do_all_sources(float(R), float(sig), float(dr), dptr(xh_av), dptr(phi_ion), int(NumSrc),
                                  int(m1), float(minlogtau), float(dlogtau), int(NumTau)))
+
+
+# ---- photo-heating rates: not in the reference's libasora (TODO at c2ray_base.py:424-426); the signatures extend
+# ---- photo_table_to_device / do_all_sources the way the CPU ray tracer takes its heating arguments -------------
+
+def heat_table_to_device(heat_thin_table, heat_thick_table, NumTau):
+    """Heating tables (radiation/blackbody.py:79-85) next to the photo tables already on the device."""
+    _f64(heat_thin_table, "heat_thin_table", int(NumTau))
+    _f64(heat_thick_table, "heat_thick_table", int(NumTau))
+    check(L.asora_heat_table_to_device(dptr(heat_thin_table), dptr(heat_thick_table), int(NumTau)))
+
+
+def do_all_sources_heat(R, coldensh_out, sig, dr, ndens, xh_av, phi_ion, phi_heat, NumSrc, m1, minlogtau, dlogtau,
+                        NumTau):
+    """do_all_sources with ``phi_heat`` (overwritten in place) after ``phi_ion``, as
+    libc2ray.raytracing.do_all_sources orders them (raytracing.f90:52-56)."""
+    if not isinstance(coldensh_out, np.ndarray) or coldensh_out.dtype != np.float64:
+        raise TypeError("coldensh_out must be Array of type double")
+    n3 = int(m1) ** 3
+    _f64(xh_av, "xh_av", n3)
+    _f64(phi_ion, "phi_ion", n3)
+    _f64(phi_heat, "phi_heat", n3)
+    if not (phi_ion.flags.writeable and phi_heat.flags.writeable):
+        raise ValueError("phi_ion and phi_heat must be writeable")
+    check(L.asora_do_all_sources_heat(float(R), float(sig), float(dr), dptr(xh_av), dptr(phi_ion), dptr(phi_heat),
+                                      int(NumSrc), int(m1), float(minlogtau), float(dlogtau), int(NumTau)))

@@ -19,9 +19,11 @@ def do_raytracing(dr, src_flux, src_pos, use_gpu, max_subbox, subboxsize, loss_f
     """Photo-ionisation rate of every cell for the current ionised fractions (no chemistry).
 
     Same arguments as the reference.  Only ``use_gpu=True`` exists in this build; the CPU-only
-    arguments (max_subbox, subboxsize, loss_fraction, heat tables) are accepted and unused.
-    Returns (phi_ion, phi_heat) with phi_heat = None, as the reference's GPU branch effectively does
-    (it returns an undefined name there: raytracing.py:106-108).
+    arguments (max_subbox, subboxsize, loss_fraction) are accepted and unused.
+    Returns (phi_ion, phi_heat).  The reference's GPU branch has no heating (it returns an undefined name
+    there: raytracing.py:106-108; TODO at c2ray_base.py:424-426); here non-zero heating tables switch the
+    photo-heating rates on (photorates.f90:118,124 evaluated in the sweep kernel), all-zero or missing tables
+    -- what C2Ray passes when ``compute_heating_rates`` is off, c2ray_base.py:431-433 -- give phi_heat = None.
     """
     if not use_gpu:
         raise NotImplementedError("CPU ray tracing is not part of this build (use_gpu must be True)")
@@ -45,7 +47,16 @@ def do_raytracing(dr, src_flux, src_pos, use_gpu, max_subbox, subboxsize, loss_f
 
     trt0 = time.time()
     printlog("Doing Raytracing...", logfile, quiet, " ")
-    libasora.do_all_sources(R_max_LLS, coldensh_out_flat, sig, dr, ndens_flat, xh_av_flat, phi_ion_flat, NumSrc, N,
-                            minlogtau, dlogtau, NumTau)
+    heating = (heat_thin_table is not None and heat_thick_table is not None
+               and (np.any(heat_thin_table) or np.any(heat_thick_table)))
+    if heating:
+        libasora.heat_table_to_device(np.ascontiguousarray(heat_thin_table, dtype=np.float64),
+                                      np.ascontiguousarray(heat_thick_table, dtype=np.float64), NumTau)
+        phi_heat_flat = np.zeros(N * N * N, dtype="float64")
+        libasora.do_all_sources_heat(R_max_LLS, coldensh_out_flat, sig, dr, ndens_flat, xh_av_flat, phi_ion_flat,
+                                     phi_heat_flat, NumSrc, N, minlogtau, dlogtau, NumTau)
+    else:
+        libasora.do_all_sources(R_max_LLS, coldensh_out_flat, sig, dr, ndens_flat, xh_av_flat, phi_ion_flat, NumSrc, N,
+                                minlogtau, dlogtau, NumTau)
     printlog(f"took {(time.time()-trt0) : .1f} s.", logfile, quiet)
-    return np.reshape(phi_ion_flat, (N, N, N)), None
+    return np.reshape(phi_ion_flat, (N, N, N)), (np.reshape(phi_heat_flat, (N, N, N)) if heating else None)
