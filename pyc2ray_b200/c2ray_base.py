@@ -105,10 +105,12 @@ class C2Ray:
 
     def do_raytracing(self, src_flux, src_pos):
         """c2ray_base.py:300-323"""
-        gamma, _ = do_raytracing(self.dr, src_flux, src_pos, True, self.max_subbox, self.subboxsize, self.loss_fraction,
-                                 self.ndens, self.xh, self.photo_thin_table, self.photo_thick_table, None, None,
-                                 self.minlogtau, self.dlogtau, self.R_max_LLS, self.sig, self.logfile)
+        gamma, heat = do_raytracing(self.dr, src_flux, src_pos, True, self.max_subbox, self.subboxsize, self.loss_fraction,
+                                    self.ndens, self.xh, self.photo_thin_table, self.photo_thick_table,
+                                    self.heat_thin_table, self.heat_thick_table, self.minlogtau, self.dlogtau,
+                                    self.R_max_LLS, self.sig, self.logfile)
         self.phi_ion = gamma
+        self.phi_heat = heat  # None unless Photo.compute_heating_rates (the reference's GPU branch has no heating)
         return gamma
 
     def printlog(self, s, quiet=False):
@@ -162,8 +164,14 @@ class C2Ray:
         self.bb_Teff = self._ld["BlackBodySource"]["Teff"]
         src = BlackBodySource(self.bb_Teff, self.grey, f_lo, self._ld["BlackBodySource"]["cross_section_pl_index"])
         self.photo_thin_table, self.photo_thick_table = src.make_photo_table(self.tau, f_lo, f_hi, 1e48)
-        self.heat_thin_table = np.zeros(self.NumTau + 1)
-        self.heat_thick_table = np.zeros(self.NumTau + 1)
+        # c2ray_base.py:384,427-433: heating tables only on request; zeros otherwise (do_raytracing then returns no
+        # heating rates)
+        self.compute_heating_rates = bool(ph.get("compute_heating_rates", False))
+        if self.compute_heating_rates:
+            self.heat_thin_table, self.heat_thick_table = src.make_heat_table(self.tau, f_lo, f_hi, 1e48)
+        else:
+            self.heat_thin_table = np.zeros(self.NumTau + 1)
+            self.heat_thick_table = np.zeros(self.NumTau + 1)
         photo_table_to_device(self.photo_thin_table, self.photo_thick_table)  # c2ray_base.py:441-443
 
     def _grid_init(self):
