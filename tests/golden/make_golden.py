@@ -84,6 +84,38 @@ def ref_heat_tables():
     print("ref_heat_tables.npz", thin.shape, thin[:2], thick[:2])
 
 
+RUN_FILES = ["xfrac_10.478.dat", "xfrac_9.938.dat", "xfrac_21.062.dat", "IonRates_9.938.dat", "xfrac_notanumber.dat"]
+SRC_FILES = ["10.478-coarsest_wsubgrid_sources.dat", "9.938-coarsest_wsubgrid_sources.dat",
+             "21.062-coarsest_wsubgrid_sources.dat", "8.515-coarsest_wsubgrid_sources.dat", "readme.txt"]
+
+
+def ref_other_utils():
+    """Redshift bookkeeping of the 244 Mpc run from the reference's own utils/other_utils.py (plain numpy/glob)."""
+    import json
+    import tempfile
+    ou = _load(os.path.join(REF, "pyc2ray/utils/other_utils.py"), "ref_other_utils")
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "results"))
+        os.makedirs(os.path.join(d, "sources"))
+        for f in RUN_FILES:
+            open(os.path.join(d, "results", f), "w").close()
+        for f in SRC_FILES:
+            open(os.path.join(d, "sources", f), "w").close()
+        out["from_output"] = [float(z) for z in ou.get_redshifts_from_output(os.path.join(d, "results") + "/")]
+        out["source_redshifts"] = [float(z) for z in ou.get_source_redshifts(os.path.join(d, "sources") + "/")]
+        out["source_redshifts_9_11"] = [float(z) for z in ou.get_source_redshifts(os.path.join(d, "sources") + "/", 9.0, 11.0)]
+        out["source_redshifts_bracket"] = [float(z) for z in
+                                           ou.get_source_redshifts(os.path.join(d, "sources") + "/", 9.0, 11.0, True)]
+    edges = [8.515, 9.938, 10.478, 21.062]
+    out["find_bins"] = {str(v): [None if b is None else float(b) for b in ou.find_bins(v, np.array(edges))]
+                        for v in (7.0, 9.0, 10.0, 15.0)}
+    out["run_files"], out["src_files"], out["edges"] = RUN_FILES, SRC_FILES, edges
+    with open(os.path.join(HERE, "ref_other_utils.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("ref_other_utils.json", out)
+
+
 def ref_sources():
     su = _load(os.path.join(REF, "pyc2ray/utils/sourceutils.py"), "ref_sourceutils")
     tmp = "/tmp/_golden_src.txt"
@@ -144,8 +176,12 @@ if __name__ == "__main__":
     if "heat" in sys.argv[1:]:
         ref_heat_tables()
         sys.exit(0)
+    if "files" in sys.argv[1:]:
+        ref_other_utils()
+        sys.exit(0)
     ref_tables()
     ref_heat_tables()
+    ref_other_utils()
     ref_sources()
     kat()
     oracle_vectors()
