@@ -100,7 +100,7 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
             check(L.asora_set_active_slab(*halo.active_range()))
             scal = torch.zeros(3, dtype=torch.float64, device="cuda")
 
-    if rank == 0:
+    if rank == 0 and not (quiet and logfile is None):  # (the two grid means below cost 22 ms at 250^3)
         printlog("Calling evolve3D..." if nprocs == 1 else f"Calling evolve3D with {nprocs:n} ranks...", logfile, quiet)
         printlog(f"dr [Mpc]: {dr/3.086e24:.3e}", logfile, quiet)
         printlog(f"dt [years]: {dt/3.15576E+07:.3e}", logfile, quiet)
