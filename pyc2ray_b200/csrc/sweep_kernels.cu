@@ -13,17 +13,18 @@
 //                         grid that stays in the 126 MB L2.  Geometry is computed on the fly.  Used
 //                         when a level does not fit in shared memory (large radii / full box).
 //
-// Arithmetic.  The first B200 profile of a literal transcription (profiles/r01_*) showed ~440
+// Arithmetic.  The first B200 profile of a literal transcription (profiles/r01a_*) showed ~440
 // thread-instructions per source-cell update, dominated by the CUDA library's fp64 division (nine per
 // update) and log10 (two per update) call sequences, with the fp64 pipe only 33-40 % busy.  The
-// per-cell arithmetic below is the same real-number computation re-associated so that one update needs
-// two reciprocals and two table-driven logarithms:
+// per-cell arithmetic below is the same real-number computation re-associated (now ~185 instructions):
 //   * the four weightf() divisions and the normalisation of raytracing.cu:422-428 become one
-//     division of products (interp_coldens);
-//   * strength/Vfact and phi/nHI (rates.cu:24, raytracing.cu:324) share one division;
+//     reciprocal of products (interp_coldens);
+//   * strength/Vfact (rates.cu:24) is a product with the plan's 1/(n path); phi/nHI (raytracing.cu:324) is the
+//     same for every source and is applied once per cell after the sweep (finish_phi_kernel);
 //   * log10(tau) -> table index (rates.cu:77-78) is index = a + b*log2(tau) with log2 from a
 //     256-entry mantissa table in shared memory and a degree-6 polynomial (|error| < 2 ulp);
-//   * T[i0] + r*(T[i1]-T[i0]) reads one 16-byte {T[i], T[i+1]-T[i]} pair.
+//   * T[i0] + r*(T[i1]-T[i0]) reads one 16-byte {T[i], T[i+1]-T[i]} pair (through the texture pipe);
+//   * int <-> double conversions by 2^52-offset additions (fp64 pipe) instead of I2F / F2I (XU pipe).
 // Results agree with the reference's own expression order to ~1e-13 relative (tests/).
 #include "asora_common.cuh"
 
@@ -359,10 +360,11 @@ __device__ __forceinline__ void sweep_level(const int4* __restrict__ plan, const
 
 // One CTA per S sources.  Per level every thread updates its cells (plan entry + opacity from global memory,
 // four upstream optical depths from the previous level's shared-memory buffer), then a CTA barrier hands
-// the level over.  Three latency-hiding variants were measured on B200 and dropped, all because the kernel
-// sits exactly at the 64-register limit that 32 resident warps allow: holding the whole next cell (plan entry
-// + opacity) in registers across the barrier (30 % slower), fetching only the 16-byte offsets stream one
-// cell ahead (10-40 % slower, spills), and prefetch.global.L1 of the next plan entry (4 % slower).
+// the level over.  Latency-hiding and staging variants that were measured on B200 and dropped ("Roofline"):
+// the whole next cell held in registers across the barrier (-30 %), the 16-byte offsets stream one cell ahead at
+// 64 registers (-10...-40 %, spills), prefetch.global.L1 of the next plan entry (-4 %), a split arrive/wait level
+// barrier (-12 %), the plan staged through shared memory by per-warp bulk copies (-19 %: fewer stalls, but 20 %
+// more instructions).  What is kept: the 4-byte offsets word one cell ahead (PF) where registers allow it.
 template <int S, int BLOCK, int MINB, int REP, bool CDOUT, bool TEX, bool PF, bool HEAT>
 __global__ void __launch_bounds__(BLOCK, MINB)
 sweep_smem_kernel(const int4* __restrict__ plan, const unsigned* __restrict__ dwords, int ncells,
