@@ -161,3 +161,75 @@ def test_gpu_heating_errors():
             libasora.heat_table_to_device(c["heat_thin"][:-1].copy(), c["heat_thick"][:-1].copy(), c["NumTau"] - 1)
     finally:
         libasora.device_close()
+
+
+@pytest.mark.gpu
+def test_gpu_heating_device_resident_entry_points():
+    """asora_set_heating + asora_raytrace_device leave the heating rates in ASORA_BUF_PHI_HEAT (no host traffic)."""
+    from pyc2ray_b200.lib import _cabi, libasora
+    L, check = _cabi.L, _cabi.check
+    c = heat_case("multi_n32")
+    N = c["N"]
+    libasora.device_init(N, 8)
+    try:
+        libasora.photo_table_to_device(c["thin"], c["thick"], c["NumTau"])
+        libasora.heat_table_to_device(c["heat_thin"], c["heat_thick"], c["NumTau"])
+        libasora.density_to_device(np.ascontiguousarray(c["ndens"].ravel()), N)
+        libasora.source_data_to_device(c["pos_flat"], c["flux_flat"], c["flux_flat"].size)
+        check(L.asora_buffer_upload(_cabi.BUF_XH_AV, _cabi.dptr(np.ascontiguousarray(c["xh"].ravel()))))
+        check(L.asora_set_heating(1))
+        check(L.asora_raytrace_device(c["R"], c["sig"], c["dr"], 0, c["flux_flat"].size, c["minlogtau"], c["dlogtau"], c["NumTau"], 1))
+        phi, heat = np.empty(N ** 3), np.empty(N ** 3)
+        check(L.asora_buffer_download(_cabi.BUF_PHI_ION, _cabi.dptr(phi)))
+        check(L.asora_buffer_download(_cabi.BUF_PHI_HEAT, _cabi.dptr(heat)))
+        with pytest.raises(RuntimeError, match="zero_phi"):
+            check(L.asora_raytrace_device(c["R"], c["sig"], c["dr"], 0, 1, c["minlogtau"], c["dlogtau"], c["NumTau"], 0))
+        check(L.asora_set_heating(0))
+        # accumulating sweeps (zero_phi = 0) without heating: two halves of the list add up to the whole
+        ns = c["flux_flat"].size
+        check(L.asora_raytrace_device(c["R"], c["sig"], c["dr"], 0, ns // 2, c["minlogtau"], c["dlogtau"], c["NumTau"], 1))
+        check(L.asora_raytrace_device(c["R"], c["sig"], c["dr"], ns // 2, ns - ns // 2, c["minlogtau"], c["dlogtau"], c["NumTau"], 0))
+        phi_halves = np.empty(N ** 3)
+        check(L.asora_buffer_download(_cabi.BUF_PHI_ION, _cabi.dptr(phi_halves)))
+    finally:
+        libasora.device_close()
+    ref_phi, ref_heat, _ = _oracle_heat(c)
+    _close(phi, ref_phi, 1e-9, "device-resident phi_ion")
+    _close(heat, ref_heat, 1e-9, "device-resident phi_heat")
+    _close(phi_halves, ref_phi, 1e-9, "phi_ion accumulated over two sweeps")
+
+
+@pytest.mark.gpu
+def test_gpu_pageable_grids_take_the_threaded_copy_path():
+    """Grids above 8 MB in pageable (numpy) memory are staged by several host threads (asora_api.cu: host_copy);
+    sizes that do not divide into whole bounce buffers, both memory orders, and pinned memory for comparison."""
+    import torch
+    from pyc2ray_b200.lib import _cabi, libasora
+    L, check = _cabi.L, _cabi.check
+    N = 113  # 113^3 * 8 B = 11.5 MB: three 4 MB chunks, the last one partial, unevenly spread over four threads
+    rng = np.random.default_rng(5)
+    a = rng.uniform(size=N ** 3)
+    libasora.device_init(N, 8)
+    try:
+        b = np.empty_like(a)
+        check(L.asora_buffer_upload(_cabi.BUF_XH, _cabi.dptr(a)))
+        check(L.asora_buffer_download(_cabi.BUF_XH, _cabi.dptr(b)))
+        np.testing.assert_array_equal(a, b)
+        af = np.asfortranarray(a.reshape(N, N, N))
+        bf = np.empty((N, N, N), order="F")
+        check(L.asora_buffer_upload_f(_cabi.BUF_TEMP, _cabi.dptr(af)))
+        check(L.asora_buffer_download_f(_cabi.BUF_TEMP, _cabi.dptr(bf)))
+        np.testing.assert_array_equal(af, bf)
+        c = np.empty(N ** 3)
+        check(L.asora_buffer_download(_cabi.BUF_TEMP, _cabi.dptr(c)))
+        np.testing.assert_array_equal(c.reshape(N, N, N), af)  # the device holds the logical C order
+        pin = torch.empty(N ** 3, dtype=torch.float64).pin_memory()
+        check(L.asora_buffer_download(_cabi.BUF_XH, ctypes_ptr(pin)))
+        np.testing.assert_array_equal(pin.numpy(), a)
+    finally:
+        libasora.device_close()
+
+
+def ctypes_ptr(t):
+    import ctypes
+    return ctypes.cast(t.data_ptr(), ctypes.POINTER(ctypes.c_double))
