@@ -27,7 +27,7 @@ def test_bench_line_contract():
     assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["unit"] == "GB/s"
     assert d["gpu_launches"] >= 2 * d["steps"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and cb["single_thread"]["value"] > 0
     assert "workload" in d["config"]
 
 
