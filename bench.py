@@ -318,6 +318,20 @@ def main():
         qmax = ctypes.c_int(0)
         L.asora_last_sweep_stats(ctypes.byref(variant), None, None, ctypes.byref(qmax), ctypes.byref(levels), None)
 
+        # ---- secondary: the same rates with the cells outside the R sphere left out (what evolve3D uses) -----
+        # phi_ion is bit-identical (tests/test_gpu_parts.py); fewer cells are swept, so this is NOT the headline:
+        # it is reported in the reference paper's own unit, time per source and sphere cell.
+        sphere_ms, sphere_updates = [], ctypes.c_int64(0)
+        check(L.asora_set_sphere_only(1))
+        for i in range(K + 1):
+            check(L.asora_raytrace_device(R, SIG, dr, 0, args.nsrc, -20.0, dlogtau, numtau, 1))
+            check(L.asora_sync())
+            ms = ctypes.c_float(0.0)
+            L.asora_last_sweep_stats(None, None, ctypes.byref(sphere_updates), None, None, ctypes.byref(ms))
+            if i > 0:
+                sphere_ms.append(ms.value)
+        check(L.asora_set_sphere_only(0))
+
         # ---- end to end through the reference-facing call, pinned host buffers ---------------------
         xh_host = torch.from_numpy(xh).pin_memory()
         phi_host = torch.zeros(N ** 3, dtype=torch.float64).pin_memory()
@@ -385,6 +399,15 @@ def main():
             "clocks": clocks,
             "phi_checksum": phi_checksum,
         }
+        sp_ms = float(np.mean(sphere_ms))
+        r_eff = min(R, N * 0.5 * 3 ** 0.5)
+        line["sphere_only"] = {
+            "ms_per_step": sp_ms, "updates_swept_per_step": int(sphere_updates.value),
+            "updates_per_s": sphere_updates.value / (sp_ms * 1e-3),
+            "ns_per_source_and_sphere_cell": sp_ms * 1e6 / (args.nsrc * 4.0 / 3.0 * np.pi * r_eff ** 3),
+            "headline_ns_per_source_and_sphere_cell": k_ms * 1e6 / (args.nsrc * 4.0 / 3.0 * np.pi * r_eff ** 3),
+            "note": "identical phi_ion, cells outside the R sphere not swept (asora_set_sphere_only); the unit is the "
+                    "reference paper's 3t/(Ns 4 pi R^3), published as 3.156 ns on a P100"}
         if eor is not None:
             line["eor_step"] = eor
         if chem is not None:
