@@ -181,8 +181,11 @@ int asora_set_sweep_variant(int variant);
  * asora_last_sweep_stats() then reports the rated cells as `updates`. */
 int asora_set_sphere_only(int sphere_only);
 
-/* Override the launch shape of the shared-memory sweep: sources per CTA (1, 2 or 4) and threads per
- * CTA (multiple of 32, <= 1024); 0 = automatic.  For tuning and profiling. */
+/* Override the launch shape of the shared-memory sweep: sources per CTA (1 or 2) and, in the low 16 bits of
+ * block_threads, threads per CTA (256, 512, 768, 896 or 1024 for one source; 256, 512 or 1024 for two); 0 =
+ * automatic.  Bits 16-18 of block_threads toggle launch options against their automatic choice (copies of the
+ * log2 table in shared memory, table gathers through the texture pipe, offsets word fetched one cell ahead);
+ * bits 20-23 force the number of parts a source is split into (1, 2, 4, 8).  For tuning and profiling. */
 int asora_set_tuning(int sources_per_cta, int block_threads);
 
 /* Statistics of the most recent ray trace: variant used, number of kernel launches, number of

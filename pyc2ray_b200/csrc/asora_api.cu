@@ -971,8 +971,8 @@ int asora_set_tuning(int sources_per_cta, int block_threads)
     g.tune_opts = (block_threads >> 16) & 7;
     g.tune_parts = (block_threads >> 20) & 15; // bits 20-23: parts per source (1, 2, 4, 8), 0 = automatic
     block_threads &= 0xffff;
-    if (!(sources_per_cta == 0 || sources_per_cta == 1 || sources_per_cta == 2 || sources_per_cta == 4))
-        return fail("set_tuning: sources_per_cta must be 0, 1, 2 or 4");
+    if (!(sources_per_cta == 0 || sources_per_cta == 1 || sources_per_cta == 2))
+        return fail("set_tuning: sources_per_cta must be 0, 1 or 2");
     if (block_threads < 0 || block_threads > 1024 || block_threads % 32) return fail("set_tuning: bad block size");
     g.tune_S = sources_per_cta;
     g.tune_block = block_threads;
