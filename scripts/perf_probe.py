@@ -34,7 +34,7 @@ N = 256
 p.device_init(N, 64)
 p.photo_table_to_device(thin, thick)
 for R in (10.0, 10.76, 30.0):
-    for S, block in ((1, 256), (1, 512), (2, 256), (2, 512), (4, 256), (4, 512), (1, 1024), (2, 1024)):
+    for S, block in ((1, 256), (1, 512), (2, 256), (2, 512), (1, 768), (1, 896), (1, 1024), (2, 1024)):
         try:
             run(N, R, 10000, "f0", S, block)
         except RuntimeError as e:

@@ -18,7 +18,7 @@ libasora.source_data_to_device(pos_flat, flux_flat, ns); libasora.density_to_dev
 check(L.asora_buffer_upload(_cabi.BUF_XH_AV, _cabi.dptr(xh)))
 for sph in (0, 1):
     check(L.asora_set_sphere_only(sph))
-    for S, block in ((0, 0), (1, 256), (2, 256), (1, 128), (2, 128), (4, 256)):
+    for S, block in ((0, 0), (1, 256), (2, 256), (1, 512), (2, 512)):
         try:
             check(L.asora_set_tuning(S, block)); best = 1e30
             for r in range(4):
