@@ -30,6 +30,30 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in _cabi.L.asora_version()
 
 
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 and a C program links against the library and calls an
+    entry point that needs no device (no torch / C++ types in the signatures)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    from pyc2ray_b200.lib import _cabi
+    hdr = os.path.join(ROOT, "include", "asora_b200.h")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    src = tmp_path / "use.c"
+    src.write_text('#include "asora_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { printf("%lld %s\\n", (long long)asora_cells_per_source(256, 30.0), asora_version());\n'
+                   '  return asora_set_heating(1) == 0; /* no device: must fail, not crash */ }\n')
+    exe = tmp_path / "use"
+    libdir = os.path.dirname(_cabi.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir,
+                    "-l:libasora_b200.so", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split()[0] == "193025" and "sm_100a" in out.stdout
+
+
 def test_cells_per_source_host_arithmetic():
     import oracle
     from pyc2ray_b200.lib import _cabi
