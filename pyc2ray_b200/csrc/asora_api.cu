@@ -386,7 +386,7 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
             if (g.grid_max_groups == 0) {
                 size_t free_b = 0, total_b = 0;
                 CK(cudaMemGetInfo(&free_b, &total_b));
-                g.grid_max_groups = (int)std::min<size_t>(16, std::max<size_t>(1, (free_b / 4) / per));
+                g.grid_max_groups = (int)std::min<size_t>(ASORA_GRID_GROUPS_MAX, std::max<size_t>(1, (free_b / 4) / per));
             }
             groups = sweep_grid_groups(p, g.grid_max_groups, nullptr, nullptr);
             if (groups < 1) return fail("sweep_grid_kernel: no resident CTAs");
@@ -399,7 +399,7 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
             }
             p.coldens_out = g.grid_scratch;
         }
-        if (!g.grid_counters) CK(cudaMalloc(&g.grid_counters, sizeof(unsigned) * 16));
+        if (!g.grid_counters) CK(cudaMalloc(&g.grid_counters, sizeof(unsigned) * ASORA_GRID_GROUPS_MAX));
     }
 
     // timed region (asora_last_sweep_stats: kernel_ms): nHI pre-pass, rate-grid zeroing, sweep

@@ -24,6 +24,9 @@
 #define ASORA_MAX_COLDENSH 2e30                         // raytracing.cu:15
 #define ASORA_TAU_PHOTO_LIMIT 1.0e-7                    // src/asora/rates.cu:7
 
+// Most concurrent sources (CTA groups, one scratch grid each) of the grid-cooperative sweep
+#define ASORA_GRID_GROUPS_MAX 74
+
 // Plan cell flags
 #define PC_RATED 1u   // inside the R_max sphere: dist2/(dr*dr) <= R*R  (raytracing.cu:315)
 #define PC_SOURCE 2u  // the source cell itself (raytracing.cu:285-294)

@@ -491,32 +491,48 @@ cudaError_t launch_sweep_smem(const SweepPlan& plan, const SweepParams& p, int S
 // variant 2: grid-cooperative level sweep, whole GPU per source
 // ---------------------------------------------------------------------------------------------------
 
-// Enumerate the cube shell max(|di|,|dj|,|dk|) == m, k fastest on the x and y faces.
-__device__ __forceinline__ void shell_cell(long long t, int m, int& di, int& dj, int& dk)
+// Enumerate the cube shell max(|di|,|dj|,|dk|) == m, k fastest on the x and y faces.  A shell has 24 m^2 + 2 <= 1.6e7
+// cells (m <= 800): everything fits 32 bits, and the divisions by the face width are 32-bit unsigned ones.
+__device__ __forceinline__ void shell_cell(unsigned t, int m, int& di, int& dj, int& dk)
 {
-    const long long w = 2 * m + 1, v = 2 * m - 1;
-    const long long fx = w * w, fy = v * w, fz = v * v;
+    const unsigned w = 2u * m + 1u, v = 2u * m - 1u;
+    const unsigned fx = w * w, fy = v * w, fz = v * v;
     if (t < 2 * fx) {
         const int sgn = (t < fx) ? 1 : -1;
         if (t >= fx) t -= fx;
+        const unsigned q = t / w;
         di = sgn * m;
-        dj = (int)(t / w) - m;
-        dk = (int)(t % w) - m;
+        dj = (int)q - m;
+        dk = (int)(t - q * w) - m;
     } else if (t < 2 * fx + 2 * fy) {
         t -= 2 * fx;
         const int sgn = (t < fy) ? 1 : -1;
         if (t >= fy) t -= fy;
+        const unsigned q = t / w;
         dj = sgn * m;
-        di = (int)(t / w) - (m - 1);
-        dk = (int)(t % w) - m;
+        di = (int)q - (m - 1);
+        dk = (int)(t - q * w) - m;
     } else {
         t -= 2 * fx + 2 * fy;
         const int sgn = (t < fz) ? 1 : -1;
         if (t >= fz) t -= fz;
+        const unsigned q = t / v;
         dk = sgn * m;
-        di = (int)(t / v) - (m - 1);
-        dj = (int)(t % v) - (m - 1);
+        di = (int)q - (m - 1);
+        dj = (int)(t - q * v) - (m - 1);
     }
+}
+
+// sqrt(x) for a normal positive x: MUFU.RSQ64H seed, two Newton steps on 1/sqrt(x), one Heron correction (<= 1 ulp).
+__device__ __forceinline__ double fast_sqrt(double x)
+{
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double h = 0.5 * x;
+    r = fma(r, fma(-h * r, r, 0.5), r);
+    r = fma(r, fma(-h * r, r, 0.5), r);
+    const double s = x * r;
+    return fma(fma(-s, s, x), 0.5 * r, s);
 }
 
 __device__ __forceinline__ int isign1(int x) { return x >= 0 ? 1 : -1; }
@@ -553,8 +569,10 @@ sweep_grid_kernel(SweepParams p, int nlevels, int ngroups, int group_ctas, unsig
     const int N = p.N;
     const int group = blockIdx.x / group_ctas;
     if (group >= ngroups) return;  // spare CTAs of an uneven split
-    const long long nthreads = (long long)group_ctas * blockDim.x;
-    const long long tid = (long long)(blockIdx.x - group * group_ctas) * blockDim.x + threadIdx.x;
+    const unsigned nthreads = (unsigned)group_ctas * blockDim.x;
+    const unsigned tid = (unsigned)(blockIdx.x - group * group_ctas) * blockDim.x + threadIdx.x;
+    // integer squared distances this far from R^2 decide the sphere test without evaluating the reference's expression
+    const double R2_lo = p.R2 * (1.0 - 1e-12), R2_hi = p.R2 * (1.0 + 1e-12);
     double* __restrict__ slab = p.coldens_out + (size_t)group * N * N * N;
     unsigned* counter = counters + group;
     unsigned epoch = 0;
@@ -564,8 +582,10 @@ sweep_grid_kernel(SweepParams p, int nlevels, int ngroups, int group_ctas, unsig
         const int i0 = p.src_pos[3 * ns + 0], j0 = p.src_pos[3 * ns + 1], k0 = p.src_pos[3 * ns + 2];
         const double sk = p.src_flux[ns] * p.kpref;
         for (int m = 0; m < nlevels; m++) {
-            const long long ncell = (m == 0) ? 1 : 24LL * m * m + 2;
-            for (long long t = tid; t < ncell; t += nthreads) {
+            const unsigned ncell = (m == 0) ? 1u : 24u * m * m + 2u;
+            // the dominant offset of every cell of level m is m: one division per level instead of five per cell
+            const double md = (double)m, inv_m = (m > 0) ? 1.0 / md : 0.0;
+            for (unsigned t = tid; t < ncell; t += nthreads) {
                 int di = 0, dj = 0, dk = 0;
                 if (m > 0) shell_cell(t, m, di, dj, dk);
                 const int ia = abs(di), ja = abs(dj), ka = abs(dk);
@@ -574,11 +594,20 @@ sweep_grid_kernel(SweepParams p, int nlevels, int ngroups, int group_ctas, unsig
                     dk > p.last_r)
                     continue;
                 unsigned flags = 0;
+                const double dn = (double)(ia * ia + ja * ja + ka * ka);
                 if (m > 0) {
-                    // sphere test in the reference's own form (raytracing.cu:302-305,315)
-                    const double xs = p.dr * (double)di, ys = p.dr * (double)dj, zs = p.dr * (double)dk;
-                    const double dist2 = __fma_rn(zs, zs, __fma_rn(ys, ys, __dmul_rn(xs, xs)));
-                    if (dist2 / (p.dr * p.dr) <= p.R2) flags |= PC_RATED;
+                    bool rated;
+                    if (dn <= R2_lo) {
+                        rated = true;
+                    } else if (dn >= R2_hi) {
+                        rated = false;
+                    } else {
+                        // on the sphere's surface to rounding: the reference's own form decides (raytracing.cu:302-305,315)
+                        const double xs = p.dr * (double)di, ys = p.dr * (double)dj, zs = p.dr * (double)dk;
+                        const double dist2 = __fma_rn(zs, zs, __fma_rn(ys, ys, __dmul_rn(xs, xs)));
+                        rated = dist2 / (p.dr * p.dr) <= p.R2;
+                    }
+                    if (rated) flags |= PC_RATED;
                     else if (p.sphere_only) continue;
                 }
                 const int i = wrap(i0 + di, N), j = wrap(j0 + dj, N), k = wrap(k0 + dk, N);
@@ -607,10 +636,14 @@ sweep_grid_kernel(SweepParams p, int nlevels, int ngroups, int group_ctas, unsig
                         q1 = im * NN + (size_t)jm * N + km; q2 = im * NN + (size_t)j * N + km;
                         q3 = im * NN + (size_t)jm * N + k;  q4 = im * NN + (size_t)j * N + k;
                     }
-                    const double dc = (double)c, da = (double)a, db = (double)b;
-                    const double wA = da / dc, wB = db / dc;
-                    path = sqrt((da * da + db * db) / (dc * dc) + 1.0);
-                    inv_np = 1.0 / ((double)(ia * ia + ja * ja + ka * ka) * path);
+                    // c == m.  wA = a/m, wB = b/m correctly rounded (reciprocal + one correction step, as in the plan-driven
+                    // sweep); path = sqrt(1 + (a^2+b^2)/c^2) = sqrt(n)/m (raytracing.cu:444); 1/(n path) by reciprocal
+                    const double da = (double)a, db = (double)b;
+                    const double qa = da * inv_m, qb = db * inv_m;
+                    const double wA = fma(fma(-md, qa, da), inv_m, qa), wB = fma(fma(-md, qb, db), inv_m, qb);
+                    const double sn = fast_sqrt(dn), qp = sn * inv_m;
+                    path = fma(fma(-md, qp, sn), inv_m, qp);
+                    inv_np = fast_rcp(dn * path);
                     if (c == 1 && (a == 1 || b == 1)) flags |= (a == 1 && b == 1) ? PC_DIAG3 : PC_DIAG2;
                     // the scratch grid is written by other SMs: read it at L2 (ld.global.cg), and skip
                     // zero-weight corners, which may never have been written for this source
@@ -628,6 +661,9 @@ sweep_grid_kernel(SweepParams p, int nlevels, int ngroups, int group_ctas, unsig
     }
 }
 
+#ifndef ASORA_GRID_MIN_CTAS
+#define ASORA_GRID_MIN_CTAS 4
+#endif
 // Number of concurrent sources (groups) for the grid-cooperative sweep, at most `max_groups` (scratch grids).
 int sweep_grid_groups(const SweepParams& p, int max_groups, int* total_ctas_out, int* group_ctas_out)
 {
@@ -646,7 +682,7 @@ int sweep_grid_groups(const SweepParams& p, int max_groups, int* total_ctas_out,
     // groups amortise the barrier over more sources (measured: scripts/perf_probe3.py), so take as many as
     // there are scratch grids and sources, keeping at least 8 CTAs per group.
     int groups = max(1, min(max_groups, p.src_count));
-    while (groups > 1 && total / groups < 8) groups--;
+    while (groups > 1 && total / groups < ASORA_GRID_MIN_CTAS) groups--;
     if (total_ctas_out) *total_ctas_out = total;
     if (group_ctas_out) *group_ctas_out = total / groups;
     return groups;
