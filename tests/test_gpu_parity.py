@@ -357,6 +357,41 @@ def test_full_size_properties_256(libs):
     _assert_close(s1, ref, "256^3 spot check vs oracle")
 
 
+def test_bench_radius_launch_shape_vs_oracle(libs):
+    """The launch shape of the headline workload (R = 30: one 896-thread CTA per SM, eight log2 copies, texture
+    gathers, offsets word one cell ahead) on a 96^3 box with non-trivial fields, against the oracle; then the same
+    sweep with every launch option toggled."""
+    oracle, p, _cabi, libasora = libs
+    from tests.fields import f1_fields, tables, SIG
+    from pyc2ray_b200.utils.sourceutils import format_sources, generate_test_sources
+    N, ns, R = 96, 12, 30.0
+    srcpos = generate_test_sources(N, ns, seed=100)
+    flux = 10 ** np.random.default_rng(11).normal(0, 0.5, size=ns)
+    ndens, xh = f1_fields(N, srcpos)
+    thin, thick, dlogtau, _ = tables("bb1e5")
+    pos_flat, flux_flat = format_sources(srcpos, flux)
+    c = dict(N=N, R=R, sig=SIG, dr=6e20, ndens=ndens, xh=xh, thin=thin, thick=thick, minlogtau=-20.0, dlogtau=dlogtau,
+             NumTau=thin.size, pos_flat=pos_flat, flux_flat=flux_flat)
+    ref, _, n = oracle.asora_do_all_sources(R, SIG, c["dr"], ndens.ravel(), xh.ravel(), pos_flat, flux_flat, N, thin, thick,
+                                            -20.0, dlogtau, thin.size)
+    _setup(libasora, c)
+    try:
+        phi, v, upd = _sweep(libasora, _cabi, c, 0)
+        assert v == 1 and upd == n
+        _assert_close(phi, ref, "R=30 default launch shape")
+        for toggle in (1, 2, 4, 7):
+            _cabi.check(_cabi.L.asora_set_tuning(0, toggle << 16))
+            alt, _, _ = _sweep(libasora, _cabi, c, 0)
+            _assert_close(alt, ref, f"R=30, launch options toggled by {toggle}")
+        for block in (768, 1024):
+            _cabi.check(_cabi.L.asora_set_tuning(1, block))
+            alt, _, _ = _sweep(libasora, _cabi, c, 0)
+            _assert_close(alt, ref, f"R=30, {block} threads")
+    finally:
+        _cabi.L.asora_set_tuning(0, 0)
+        libasora.device_close()
+
+
 def test_do_raytracing_wrapper(libs):
     """pyc2ray_b200.do_raytracing (pyc2ray/raytracing.py:34-108): 1-indexed (3,Ns) sources, 3-D grids in any
     memory order, returns phi_ion of shape (N,N,N)."""
