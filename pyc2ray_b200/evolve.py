@@ -14,7 +14,8 @@ import numpy as np
 from .asora_core import cuda_is_init
 from .lib import _cabi
 from .lib._cabi import L, check, dptr, iptr
-from .parallel import shard_bounds, allreduce_sum_, device_tensor, slab_edges, SlabHalo
+from .parallel import (shard_bounds, allreduce_sum_, reduce_scatter_sum_, allgather_chunks_, device_tensor, slab_edges,
+                       SlabHalo)
 from .utils import printlog
 from .utils.sourceutils import format_sources
 
@@ -75,6 +76,11 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
         rank, nprocs = 0, 1
         srcpos_flat, normflux_flat = format_sources(src_pos, src_flux)
     NumSrc = normflux_flat.shape[0]
+    # List-order sharding, optimised exchange: reduce-scatter of phi_ion, chemistry on the rank's own
+    # N^3/nprocs cells, all-gather of the new xh_av -- the bytes of one all-reduce, 1/nprocs of the chemistry.
+    rsag = (nprocs > 1 and halo is None and decomposition in ("auto", "rsag") and NumCells % nprocs == 0)
+    if decomposition == "rsag" and nprocs > 1 and not rsag:
+        raise ValueError("rsag decomposition needs N^3 divisible by the number of ranks")
 
     check(L.asora_source_data_to_device(iptr(srcpos_flat), dptr(normflux_flat), NumSrc))
     if halo is None or _is_f(ndens) or _is_f(temp) or _is_f(xh):
@@ -95,6 +101,10 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
     if nprocs > 1:
         import torch
         phi_t = device_tensor(L.asora_device_buffer(_cabi.BUF_PHI_ION), NumCells)
+        if rsag:
+            xav_t = device_tensor(L.asora_device_buffer(_cabi.BUF_XH_AV), NumCells)
+            scal = torch.zeros(3, dtype=torch.float64, device="cuda")
+            chunk = NumCells // nprocs
         if halo is not None:
             xav_t = device_tensor(L.asora_device_buffer(_cabi.BUF_XH_AV), NumCells)
             check(L.asora_set_active_slab(*halo.active_range()))
@@ -126,6 +136,9 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
             if halo is not None:
                 halo.reduce_phi_(phi_t)       # neighbours' rates for my planes: 2 halos of h*N^2 doubles
                 torch.cuda.synchronize()
+            elif rsag:
+                reduce_scatter_sum_(phi_t, rank, nprocs, group)  # my chunk of the summed rates
+                torch.cuda.synchronize()
             elif nprocs > 1:
                 allreduce_sum_(phi_t, group)  # evolve.py:433-437 (Reduce + Bcast) as one NCCL all-reduce
                 torch.cuda.synchronize()
@@ -139,6 +152,16 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
                 scal.copy_(torch.tensor([flag.value, s1.value, s0.value], dtype=torch.float64))
                 allreduce_sum_(scal, group)   # conv_flag, sum x, sum 1-x over all planes
                 halo.gather_xh_(xav_t)        # my neighbours' new xh_av inside my ray-tracing reach
+                torch.cuda.synchronize()
+                g = scal.tolist()
+                conv_flag, sum_xh1_int, sum_xh0_int = int(round(g[0])), g[1], g[2]
+            elif rsag:
+                check(L.asora_global_pass_device_range(float(dt), float(bh00), float(albpow), float(colh0), float(temph0),
+                                                       float(abu_c), rank * chunk, chunk, ctypes.byref(flag), ctypes.byref(s1),
+                                                       ctypes.byref(s0)))
+                scal.copy_(torch.tensor([flag.value, s1.value, s0.value], dtype=torch.float64))
+                allreduce_sum_(scal, group)                     # conv_flag, sum x, sum 1-x over all chunks
+                allgather_chunks_(xav_t, rank, nprocs, group)   # every rank sweeps with the whole new xh_av
                 torch.cuda.synchronize()
                 g = scal.tolist()
                 conv_flag, sum_xh1_int, sum_xh0_int = int(round(g[0])), g[1], g[2]
@@ -164,6 +187,11 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
         L.asora_set_sphere_only(0)
         if halo is not None:
             L.asora_set_active_slab(0, 0)
+    if rsag:
+        # once per time step: every rank gets the whole grids back (the reference API returns full arrays)
+        allgather_chunks_(device_tensor(L.asora_device_buffer(_cabi.BUF_XH_INTERMED), NumCells), rank, nprocs, group)
+        allgather_chunks_(phi_t, rank, nprocs, group)
+        torch.cuda.synchronize()
     if halo is not None:
         # once per time step: every rank gets the whole grids back (the reference API returns full arrays)
         halo.assemble_(device_tensor(L.asora_device_buffer(_cabi.BUF_XH_INTERMED), NumCells))
@@ -211,10 +239,12 @@ def evolve3D_dist(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table, 
     (backend nccl, one rank per GPU).  Every rank passes the full source list and gets the full
     result.
 
-    decomposition: "list" -- contiguous blocks of the source list and one all-reduce of phi_ion per iteration
-    (the reference's scheme, evolve.py:360-373,433-437); "slab" -- sources sharded by position, halo exchanges
-    instead of N^3 collectives (parallel.SlabHalo); "auto" -- slab when the slabs are wide enough for the
-    ray-tracing radius, else list."""
+    decomposition: "list" -- contiguous blocks of the source list, one all-reduce of phi_ion per iteration and the
+    chemistry of the whole grid on every rank (the reference's scheme, evolve.py:360-373,433-437, minus its rank-0
+    chemistry and broadcasts); "rsag" -- the same sharding with a reduce-scatter of phi_ion, chemistry on the rank's
+    N^3/nprocs cells and an all-gather of xh_av; "slab" -- sources sharded by position, halo exchanges
+    instead of N^3 collectives (parallel.SlabHalo); "auto" -- slab when the slabs are wide enough for the ray-tracing
+    radius, else rsag when N^3 divides by the number of ranks, else list."""
     import torch.distributed as dist
     rank, nprocs = dist.get_rank(group), dist.get_world_size(group)
     shard = (rank, nprocs) if src_flux.shape[0] >= nprocs else None  # c2ray_base.py:185

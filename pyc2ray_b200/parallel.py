@@ -8,7 +8,7 @@ chemistry pass on the full grid, which replaces the reference's rank-0 chemistry
 """
 import numpy as np
 
-__all__ = ["shard_bounds", "allreduce_sum_", "DeviceView", "device_tensor"]
+__all__ = ["shard_bounds", "allreduce_sum_", "reduce_scatter_sum_", "allgather_chunks_", "DeviceView", "device_tensor"]
 
 
 def shard_bounds(NumSrc, rank, nprocs):
@@ -24,6 +24,30 @@ def allreduce_sum_(tensor, group=None):
     import torch.distributed as dist
     dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=group)
     return tensor
+
+
+def reduce_scatter_sum_(full, rank, nprocs, group=None):
+    """Sum over ranks of ``full`` (n doubles, n divisible by nprocs), leaving rank r's chunk r summed in place; the
+    other chunks of ``full`` are garbage afterwards.  NCCL: one in-place reduce-scatter (half the traffic of an
+    all-reduce); gloo has no reduce-scatter, so the CPU host-logic tests use an all-reduce, which leaves the same
+    chunk.  Returns the rank's chunk (a view)."""
+    import torch.distributed as dist
+    n = full.numel() // nprocs
+    mine = full[rank * n:(rank + 1) * n]
+    if full.is_cuda:
+        dist.reduce_scatter_tensor(mine, full, op=dist.ReduceOp.SUM, group=group)
+    else:
+        dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)
+    return mine
+
+
+def allgather_chunks_(full, rank, nprocs, group=None):
+    """Every rank contributes its chunk of ``full`` (in place); afterwards all ranks hold the whole tensor."""
+    import torch.distributed as dist
+    n = full.numel() // nprocs
+    dist.all_gather_into_tensor(full, full[rank * n:(rank + 1) * n].clone() if not full.is_cuda else full[rank * n:(rank + 1) * n],
+                                group=group)
+    return full
 
 
 class DeviceView:

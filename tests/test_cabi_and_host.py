@@ -160,8 +160,20 @@ def _rank_main(rank, world, port, outdir):
     phi, _, _ = oracle.asora_do_all_sources(c["R"], c["sig"], c["dr"], c["ndens"].ravel(), c["xh"].ravel(), pos_flat, flux_flat,
                                             c["N"], c["thin"], c["thick"], c["minlogtau"], c["dlogtau"], c["NumTau"])
     t = torch.from_numpy(phi)
+    t2 = t.clone()
     allreduce_sum_(t)
     np.save(os.path.join(outdir, f"phi_{rank}.npy"), t.numpy())
+    # the reduce-scatter / all-gather exchange (evolve3D_dist, decomposition "rsag"): my chunk of the sum, then the
+    # chunks of all ranks put together again
+    from pyc2ray_b200.parallel import reduce_scatter_sum_, allgather_chunks_
+    mine = reduce_scatter_sum_(t2, rank, world)
+    n = t2.numel() // world
+    assert mine.data_ptr() == t2[rank * n:(rank + 1) * n].data_ptr()
+    assert torch.equal(mine, t[rank * n:(rank + 1) * n])
+    t2[:rank * n] = -1.0            # only the rank's own chunk may be used
+    t2[(rank + 1) * n:] = -1.0
+    allgather_chunks_(t2, rank, world)
+    assert torch.equal(t2, t)
     dist.destroy_process_group()
 
 

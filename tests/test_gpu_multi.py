@@ -80,3 +80,22 @@ def test_two_gpu_slab_decomposition_matches_single_gpu(tmp_path):
     assert xs.mean() > 3e-4
     np.testing.assert_allclose(x0, xs, rtol=1e-10, atol=1e-16)
     np.testing.assert_allclose(p0, ps, rtol=1e-10, atol=1e-12 * ps.max())
+
+
+def test_two_gpu_reduce_scatter_decomposition_matches_single_gpu(tmp_path):
+    """List-order sharding with reduce-scatter -> chemistry on the rank's own cells -> all-gather."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(2, port, str(tmp_path), "rsag"), nprocs=2, join=True)
+    x0, x1, xs = (np.load(tmp_path / f) for f in ("x_0.npy", "x_1.npy", "x_single.npy"))
+    p0, p1, ps = (np.load(tmp_path / f) for f in ("phi_0.npy", "phi_1.npy", "phi_single.npy"))
+    np.testing.assert_array_equal(x0, x1)
+    np.testing.assert_array_equal(p0, p1)
+    np.testing.assert_allclose(x0, xs, rtol=1e-10, atol=1e-16)
+    np.testing.assert_allclose(p0, ps, rtol=1e-10, atol=1e-12 * ps.max())
