@@ -33,7 +33,7 @@ phi = np.zeros(N ** 3); dummy = np.zeros(1)
 for R in (10.0, 30.0):
     cells = int(_cabi.L.asora_cells_per_source(N, R))
     sphere = 4.0 / 3.0 * np.pi * R ** 3
-    for batch in (64, 128):
+    for batch in (32, 64, 96, 128):
         assert R_.ref_device_init(N, batch) == 0
         R_.ref_density_to_device(ndens.ctypes.data_as(dp), N)
         R_.ref_photo_table_to_device(thin.ctypes.data_as(dp), thick.ctypes.data_as(dp), 20000)
