@@ -394,6 +394,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "sweep_smem_kernel" if variant.value == 1 else "sweep_grid_kernel",
                          "kernel_ms": k_ms, "bytes_per_update": BYTES_PER_UPDATE, "peak_source": peak_src,
+                         "kernel_ms_scope": "CUDA events on the launching stream around the sweep kernel and its three small "
+                                            "companions (opacity pre-pass, zeroing, division pass: 0.15 ms together)",
                          "traffic_unit": "bytes per launch (ncu dram__bytes_read+write)",
                          "note": "bound by instruction issue and the L1 data pipe, not by HBM (L2 hit rate 92 %): see DESIGN.md and profiles/README.md"},
             "clocks": clocks,
