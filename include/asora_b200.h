@@ -185,14 +185,20 @@ int asora_set_sphere_only(int sphere_only);
  * block_threads, threads per CTA (256, 512, 768, 896 or 1024 for one source; 256, 512 or 1024 for two); 0 =
  * automatic.  Bits 16-18 of block_threads toggle launch options against their automatic choice (copies of the
  * log2 table in shared memory, table gathers through the texture pipe, offsets word fetched one cell ahead);
+ * bit 19 toggles the (k,i,j)-ordered grid copies for z-face cells (automatic only for sweeps of >= 5e8 updates);
  * bits 20-23 force the number of parts a source is split into (1, 2, 4, 8).  For tuning and profiling. */
 int asora_set_tuning(int sources_per_cta, int block_threads);
 
 /* Statistics of the most recent ray trace: variant used, number of kernel launches, number of
  * (source, cell) updates, q_max, number of Chebyshev levels, device milliseconds (CUDA events on
- * the context's stream around the sweep kernel(s) only).  Any pointer may be NULL. */
+ * the context's stream around the whole sweep: opacity pre-pass, zeroing, sweep kernel, division pass).
+ * Any pointer may be NULL. */
 int asora_last_sweep_stats(int* variant, int* launches, int64_t* updates, int* q_max, int* levels,
                            float* kernel_ms);
+
+/* Device milliseconds of the sweep kernel of the most recent ray trace alone (CUDA events on the launching
+ * stream right before and after that one launch). */
+int asora_last_sweep_kernel_ms(float* kernel_only_ms);
 
 /* Number of cells the sweep visits per source: |octahedron(q_max) & cube| (raytracing.cu:101,
  * 122-123,241).  Pure host arithmetic; needs no device. */

@@ -26,9 +26,11 @@ struct Context {
     int sm_count = 0;
     int smem_optin = 0;
     int smem_per_sm = 0;
+    bool zface_ok = false;     // 2 N^3 < 2^32: the (k,i,j)-ordered copies of nhi / phi fit the 32-bit cell positions
     cudaStream_t stream = nullptr;      // the stream work is queued on
     cudaStream_t own_stream = nullptr;  // created by device_init; `stream` unless the caller set one
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // around a whole sweep: pre-pass, zeroing, sweep kernel, division pass
+    cudaEvent_t evk0 = nullptr, evk1 = nullptr; // around the sweep kernel alone
     double* buf[ASORA_BUF_COUNT] = {nullptr};
     double2* thin = nullptr;   // {T[i], T[i+1]-T[i]} pairs (sweep_kernels.cu: photo_lookup)
     double2* thick = nullptr;
@@ -124,8 +126,11 @@ int ensure_buffer(int which)
 {
     if (which < 0 || which >= ASORA_BUF_COUNT) return fail("unknown buffer id");
     if (!g.buf[which]) {
-        CK(cudaMalloc(&g.buf[which], sizeof(double) * g.ncell));
-        CK(cudaMemsetAsync(g.buf[which], 0, sizeof(double) * g.ncell, g.stream));
+        // the rate grids carry a second, (k,i,j)-ordered half for the z-face cells of large sweeps (run_sweep)
+        const bool twice = g.zface_ok && (which == ASORA_BUF_PHI_ION || which == ASORA_BUF_PHI_HEAT);
+        const size_t n = (size_t)g.ncell * (twice ? 2 : 1);
+        CK(cudaMalloc(&g.buf[which], sizeof(double) * n));
+        CK(cudaMemsetAsync(g.buf[which], 0, sizeof(double) * n, g.stream));
     }
     return 0;
 }
@@ -245,7 +250,7 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     if (int rc = ensure_buffer(ASORA_BUF_XH_AV)) return rc;
     if (int rc = ensure_buffer(ASORA_BUF_PHI_ION)) return rc;
     const int N = g.N;
-    if (!g.nhi) CK(cudaMalloc(&g.nhi, sizeof(double) * g.ncell));
+    if (!g.nhi) CK(cudaMalloc(&g.nhi, sizeof(double) * g.ncell * (g.zface_ok ? 2 : 1)));
     if (!g.log2_tab) {
         double h[512];
         host_log2_table(h);
@@ -370,7 +375,7 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
                 // threads: 1.21 -> 1.11 ms; R = 30, 1024 threads: 18.2 -> 18.9 ms) -- scripts/perf_probe6.py
                 opts |= 2;
                 if (block == 256 || block == 896) opts |= 4;
-                opts ^= g.tune_opts;  // profiling knob: bits 16-18 of set_tuning's block_threads toggle the options
+                opts ^= (g.tune_opts & 7);  // profiling knob: bits 16-18 of set_tuning's block_threads toggle the options
             }
         }
         if (variant == 1 && !plan_ok) return fail("sweep variant 1 forced but a level does not fit in shared memory");
@@ -402,6 +407,16 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
         if (!g.grid_counters) CK(cudaMalloc(&g.grid_counters, sizeof(unsigned) * ASORA_GRID_GROUPS_MAX));
     }
 
+    // Large shared-memory sweeps read the opacity and add the rates of their z-face cells through (k,i,j)-ordered
+    // copies of the two grids: a third of all cells, whose warps otherwise touch 32 sectors per gather and per RED
+    // (R = 30: 17.5 -> 16.4 ms with two extra transposing passes of 0.1 ms each).  Not for short sweeps, which would not
+    // recover the passes, nor for slab-decomposed runs, whose plane ranges are not contiguous in the copies.
+    const bool slab_active = g.slab_count > 0 && g.slab_count < N;
+    bool use_z = variant == 1 && S == 1 && block >= 768 && g.zface_ok && !coldens_grid && !slab_active && g.plan.nlevels >= 24 &&
+                 (double)count * (double)(g.plan.ncells / g.plan.parts) >= 5e8;
+    if (g.tune_opts & 8) use_z = !use_z && variant == 1 && S == 1 && block >= 768 && g.zface_ok && !coldens_grid && !slab_active;  // profiling knob
+    p.zface_offset = use_z ? (unsigned)g.ncell : 0u;
+
     // timed region (asora_last_sweep_stats: kernel_ms): nHI pre-pass, rate-grid zeroing, sweep
     CK(cudaEventRecord(g.ev0, g.stream));
     {
@@ -416,12 +431,20 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
             seg_off[1] = 0;
             seg_len[1] = (g.slab_count - first) * plane;
         }
+        if (use_z) {  // whole grid (no slab): opacity and its (k,i,j)-ordered copy in one pass
+            cudaError_t e = launch_prepare_nhi_transposed(g.buf[ASORA_BUF_NDENS], g.buf[ASORA_BUF_XH_AV], g.nhi, g.nhi + g.ncell,
+                                                          sig * dr, N, g.stream);
+            if (e != cudaSuccess) return fail_cuda("prepare_nhi_transposed_kernel launch", e);
+            g.last_launches += 1;
+            CK(cudaMemsetAsync(g.buf[ASORA_BUF_PHI_ION] + g.ncell, 0, sizeof(double) * g.ncell, g.stream));
+            if (p.phi_heat) CK(cudaMemsetAsync(p.phi_heat + g.ncell, 0, sizeof(double) * g.ncell, g.stream));
+        }
         for (int sg = 0; sg < 2; sg++) {
             if (seg_len[sg] <= 0) continue;
-            cudaError_t e = launch_prepare_nhi(g.buf[ASORA_BUF_NDENS] + seg_off[sg], g.buf[ASORA_BUF_XH_AV] + seg_off[sg],
+            cudaError_t e = use_z ? cudaSuccess : launch_prepare_nhi(g.buf[ASORA_BUF_NDENS] + seg_off[sg], g.buf[ASORA_BUF_XH_AV] + seg_off[sg],
                                                g.nhi + seg_off[sg], sig * dr, seg_len[sg], g.stream);
             if (e != cudaSuccess) return fail_cuda("prepare_nhi_kernel launch", e);
-            g.last_launches += 1;
+            if (!use_z) g.last_launches += 1;
             // the sweep accumulates undivided sums in phi_ion (finish_cell); earlier rates wait in phi_keep
             if (!zero_phi) {
                 if (!g.phi_keep) CK(cudaMalloc(&g.phi_keep, sizeof(double) * g.ncell));
@@ -433,6 +456,7 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
         }
     }
 
+    CK(cudaEventRecord(g.evk0, g.stream));
     if (variant == 1) {
         g.last_levels = g.plan.nlevels;
         cudaError_t e = launch_sweep_smem(g.plan, p, S, block, opts, g.stream, &g.last_launches);
@@ -441,6 +465,7 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
         cudaError_t e = launch_sweep_grid(p, groups, g.grid_counters, g.stream, &g.last_launches, &g.last_levels);
         if (e != cudaSuccess) return fail_cuda("sweep_grid_kernel launch", e);
     }
+    CK(cudaEventRecord(g.evk1, g.stream));
     {   // phi = sum / ntau over the planes the sweep could touch
         const int64_t plane = (int64_t)N * N;
         int64_t seg_off[2] = {0, 0}, seg_len[2] = {g.ncell, 0};
@@ -451,7 +476,17 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
             seg_len[0] = first * plane;
             seg_len[1] = (g.slab_count - first) * plane;
         }
-        for (int sg = 0; sg < 2; sg++) {
+        if (use_z) {
+            cudaError_t e = launch_finish_phi_transposed(g.buf[ASORA_BUF_PHI_ION], g.buf[ASORA_BUF_PHI_ION] + g.ncell, g.nhi,
+                                                         zero_phi ? nullptr : g.phi_keep, N, g.stream);
+            g.last_launches += 1;
+            if (e == cudaSuccess && p.phi_heat) {
+                e = launch_finish_phi_transposed(p.phi_heat, p.phi_heat + g.ncell, g.nhi, nullptr, N, g.stream);
+                g.last_launches += 1;
+            }
+            if (e != cudaSuccess) return fail_cuda("finish_phi_transposed_kernel launch", e);
+        }
+        for (int sg = 0; sg < 2 && !use_z; sg++) {
             if (seg_len[sg] <= 0) continue;
             cudaError_t e = launch_finish_phi(g.buf[ASORA_BUF_PHI_ION] + seg_off[sg], g.nhi + seg_off[sg],
                                               zero_phi ? nullptr : g.phi_keep + seg_off[sg], seg_len[sg], g.stream);
@@ -482,6 +517,15 @@ const char* asora_version(void) { return "asora_b200 0.1 (sm_100a)"; }
 
 int64_t asora_cells_per_source(int N, double R) { return asora_count_cells(N, R); }
 
+int asora_last_sweep_kernel_ms(float* kernel_only_ms)
+{
+    if (int rc = need_init()) return rc;
+    if (!kernel_only_ms) return fail("last_sweep_kernel_ms: null pointer");
+    CK(cudaEventSynchronize(g.evk1));
+    CK(cudaEventElapsedTime(kernel_only_ms, g.evk0, g.evk1));
+    return 0;
+}
+
 int asora_device_init(int N, int num_src_par)
 {
     (void)num_src_par;
@@ -496,10 +540,13 @@ int asora_device_init(int N, int num_src_par)
     CK(cudaDeviceGetAttribute(&g.smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, g.device));
     g.N = N;
     g.ncell = (int64_t)N * N * N;
+    g.zface_ok = 2 * g.ncell < ((int64_t)1 << 32);
     CK(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
     g.stream = g.own_stream;
     CK(cudaEventCreate(&g.ev0));
     CK(cudaEventCreate(&g.ev1));
+    CK(cudaEventCreate(&g.evk0));
+    CK(cudaEventCreate(&g.evk1));
     g.init = true;
     // the three grids the reference allocates up front (memory.cu:66-68)
     if (int rc = ensure_buffer(ASORA_BUF_NDENS)) return rc;
@@ -575,6 +622,9 @@ int asora_device_close(void)
     free_sweep_plan(g.plan);
     if (g.ev0) cudaEventDestroy(g.ev0);
     if (g.ev1) cudaEventDestroy(g.ev1);
+    if (g.evk0) cudaEventDestroy(g.evk0);
+    if (g.evk1) cudaEventDestroy(g.evk1);
+    g.evk0 = g.evk1 = nullptr;
     if (g.own_stream) cudaStreamDestroy(g.own_stream);
     g.ev0 = g.ev1 = nullptr;
     g.stream = g.own_stream = nullptr;
@@ -801,7 +851,7 @@ int asora_buffer_upload_f(int which, const double* host_fortran)
     if (int rc = need_init()) return rc;
     if (int rc = ensure_buffer(which)) return rc;
     if (!host_fortran) return fail("buffer_upload_f: null pointer");
-    if (!g.nhi) CK(cudaMalloc(&g.nhi, sizeof(double) * g.ncell));
+    if (!g.nhi) CK(cudaMalloc(&g.nhi, sizeof(double) * g.ncell * (g.zface_ok ? 2 : 1)));
     if (which == ASORA_BUF_TEMP) g.chem_factors_valid = false;
     if (int rc = host_copy(g.nhi, host_fortran, sizeof(double) * g.ncell, cudaMemcpyHostToDevice)) return rc;
     cudaError_t e = launch_reverse_axes(g.nhi, g.buf[which], g.N, g.stream);
@@ -815,7 +865,7 @@ int asora_buffer_download_f(int which, double* host_fortran)
     if (int rc = need_init()) return rc;
     if (int rc = ensure_buffer(which)) return rc;
     if (!host_fortran) return fail("buffer_download_f: null pointer");
-    if (!g.nhi) CK(cudaMalloc(&g.nhi, sizeof(double) * g.ncell));
+    if (!g.nhi) CK(cudaMalloc(&g.nhi, sizeof(double) * g.ncell * (g.zface_ok ? 2 : 1)));
     cudaError_t e = launch_reverse_axes(g.buf[which], g.nhi, g.N, g.stream);
     if (e != cudaSuccess) return fail_cuda("reverse_axes_kernel launch", e);
     return host_copy(host_fortran, g.nhi, sizeof(double) * g.ncell, cudaMemcpyDeviceToHost);
@@ -968,7 +1018,7 @@ int asora_set_tuning(int sources_per_cta, int block_threads)
 {
     // bits 16-18 of block_threads toggle launch options of the shared-memory sweep (profiling knob): 16 = copies of
     // the log2 table, 17 = table gathers through the texture pipe, 18 = offsets word fetched one cell ahead
-    g.tune_opts = (block_threads >> 16) & 7;
+    g.tune_opts = (block_threads >> 16) & 15;  // bit 19 toggles the z-face copies
     g.tune_parts = (block_threads >> 20) & 15; // bits 20-23: parts per source (1, 2, 4, 8), 0 = automatic
     block_threads &= 0xffff;
     if (!(sources_per_cta == 0 || sources_per_cta == 1 || sources_per_cta == 2))

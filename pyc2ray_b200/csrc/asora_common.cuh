@@ -32,6 +32,7 @@
 #define PC_SOURCE 2u  // the source cell itself (raytracing.cu:285-294)
 #define PC_DIAG2 4u   // incoming column scaled by sqrt(2) (raytracing.cu:431-441)
 #define PC_DIAG3 8u   // incoming column scaled by sqrt(3)
+#define PC_ZFACE 16u  // interior of a z face of its level (|dk| = m > |di|, |dj|): consecutive cells step in j, not in k
 
 // One cell of the sweep plan on the host (48 bytes); the device copy keeps 32 of them (two 16-byte streams).
 struct __align__(16) PlanCell {
@@ -94,6 +95,7 @@ struct SweepParams {
     const double* src_flux;
     int src_begin, src_count;
     int sphere_only;          // grid-cooperative variant: skip cells outside the R sphere
+    unsigned zface_offset;    // != 0: z-face cells use the (k,i,j)-ordered copies of nhi / phi this many doubles behind them
     double* coldens_out;      // optional N^3 grid receiving outgoing optical depths (debug) or
                               // the L2-resident scratch of the grid-cooperative variant
 };
@@ -139,6 +141,10 @@ cudaError_t launch_sweep_grid(const SweepParams& p, int ngroups, unsigned* count
 cudaError_t launch_prepare_nhi(const double* ndens, const double* xh_av, double* ntau, double sig_dr, int64_t ncell,
                                cudaStream_t stream);
 cudaError_t launch_finish_phi(double* phi, const double* ntau, const double* keep, int64_t ncell, cudaStream_t stream);
+cudaError_t launch_prepare_nhi_transposed(const double* ndens, const double* xh_av, double* ntau, double* ntau_t, double sig_dr,
+                                          int N, cudaStream_t stream);
+cudaError_t launch_finish_phi_transposed(double* phi, const double* phi_t, const double* ntau, const double* keep, int N,
+                                         cudaStream_t stream);
 cudaError_t launch_reverse_axes(const double* in, double* out, int N, cudaStream_t stream);
 cudaError_t launch_scale_grid(double* grid, double factor, int64_t ncell, cudaStream_t stream);
 cudaError_t launch_pair_table(const double* table, double2* pairs, int ntab, cudaStream_t stream);

@@ -285,19 +285,24 @@ struct Fetched {
 // third 512-byte load per warp on the L1 data pipe.
 // wrapX/Y/Z: per-source shared-memory tables, indexed by the biased offset, holding the periodic
 // cell coordinate already multiplied by its stride (N*N, N, 1): one LDS per axis replaces the
-// add / sign-fix / compare / select chain of modulo_gpu (raytracing.cu:24,270-272).
+// add / sign-fix / compare / select chain of modulo_gpu (raytracing.cu:24,270-272).  A second set of tables serves
+// the cells in the interior of a level's z faces (PC_ZFACE): there consecutive cells step in j, a stride of N doubles in
+// the (i,j,k) grids, so a warp's opacity gather and its RED touch 32 sectors each; the second set addresses (k,i,j)-ordered
+// copies of the two grids (strides N, 1, N*N plus the offset of the copies), where the same warp touches two runs of 16
+// consecutive doubles.  Only the ZF instantiations (one CTA per SM shapes of large radii) carry this.
 // PF: `dword` ({d[3], flags}, the third word of the second stream) was fetched one cell ahead from its own 4-byte
 // stream, so the opacity gather starts together with the plan loads instead of after them.
-template <int S, bool PF>
+template <int S, bool PF, bool ZF>
 __device__ __forceinline__ void fetch_cell(Fetched<S>& f, const int4* __restrict__ plan, int ncells, int e, unsigned dword,
                                            double md, double inv_m, const unsigned* __restrict__ wrap_tab, int side,
                                            const double* __restrict__ nhi)
 {
     if (PF) {
         const unsigned di = dword & 0xff, dj = (dword >> 8) & 0xff, dk = (dword >> 16) & 0xff;
+        const unsigned* wz = ZF ? wrap_tab + ((dword >> 28) & 1u) * (3 * S * side) : wrap_tab;  // PC_ZFACE: second set
 #pragma unroll
         for (int s = 0; s < S; s++) {
-            const unsigned* w = wrap_tab + 3 * s * side;
+            const unsigned* w = wz + 3 * s * side;
             f.pos[s] = w[di] + w[side + dj] + w[2 * side + dk];
             f.nhi[s] = __ldg(nhi + f.pos[s]);
         }
@@ -317,9 +322,10 @@ __device__ __forceinline__ void fetch_cell(Fetched<S>& f, const int4* __restrict
     f.wB = fma(fma(-md, qb, db), inv_m, qb);
     if (!PF) {
         const unsigned di = rb.z & 0xff, dj = (rb.z >> 8) & 0xff, dk = (rb.z >> 16) & 0xff;
+        const unsigned* wz = ZF ? wrap_tab + (((unsigned)rb.z >> 28) & 1u) * (3 * S * side) : wrap_tab;
 #pragma unroll
         for (int s = 0; s < S; s++) {
-            const unsigned* w = wrap_tab + 3 * s * side;
+            const unsigned* w = wz + 3 * s * side;
             f.pos[s] = w[di] + w[side + dj] + w[2 * side + dk];  // N <= 1600: fits 32 bits
             f.nhi[s] = __ldg(nhi + f.pos[s]);
         }
@@ -327,7 +333,7 @@ __device__ __forceinline__ void fetch_cell(Fetched<S>& f, const int4* __restrict
 }
 
 // One level of the sweep for the S sources of a CTA.
-template <int S, int BLOCK, int REP, bool DIAG, bool CDOUT, bool TEX, bool PF, bool HEAT>
+template <int S, int BLOCK, int REP, bool DIAG, bool CDOUT, bool TEX, bool PF, bool HEAT, bool ZF>
 __device__ __forceinline__ void sweep_level(const int4* __restrict__ plan, const unsigned* __restrict__ dwords, int ncells,
                                             int beg, int end, int m, double* __restrict__ cur,
                                             const double* __restrict__ prev, int max_level_cells,
@@ -343,7 +349,7 @@ __device__ __forceinline__ void sweep_level(const int4* __restrict__ plan, const
         unsigned dnext = 0;
         if (PF && e + BLOCK < end) dnext = __ldg(dwords + e + BLOCK);
         Fetched<S> c;
-        fetch_cell<S, PF>(c, plan, ncells, e, dword, md, inv_m, wrap_tab, side, p.nhi);
+        fetch_cell<S, PF, ZF>(c, plan, ncells, e, dword, md, inv_m, wrap_tab, side, p.nhi);
         const int slot = e - beg;
 #pragma unroll
         for (int s = 0; s < S; s++) {
@@ -365,7 +371,7 @@ __device__ __forceinline__ void sweep_level(const int4* __restrict__ plan, const
 // 64 registers (-10...-40 %, spills), prefetch.global.L1 of the next plan entry (-4 %), a split arrive/wait level
 // barrier (-12 %), the plan staged through shared memory by per-warp bulk copies (-19 %: fewer stalls, but 20 %
 // more instructions).  What is kept: the 4-byte offsets word one cell ahead (PF) where registers allow it.
-template <int S, int BLOCK, int MINB, int REP, bool CDOUT, bool TEX, bool PF, bool HEAT>
+template <int S, int BLOCK, int MINB, int REP, bool CDOUT, bool TEX, bool PF, bool HEAT, bool ZF>
 __global__ void __launch_bounds__(BLOCK, MINB)
 sweep_smem_kernel(const int4* __restrict__ plan, const unsigned* __restrict__ dwords, int ncells,
                   const int* __restrict__ level_start_all,
@@ -374,7 +380,7 @@ sweep_smem_kernel(const int4* __restrict__ plan, const unsigned* __restrict__ dw
     extern __shared__ double2 sh_raw[];
     double2* log2_all = sh_raw;                                        // 256 entries x REP copies
     double* sh_cd = reinterpret_cast<double*>(sh_raw + 256 * REP);     // [2][S][max_level_cells]
-    unsigned* wrap_tab = reinterpret_cast<unsigned*>(sh_cd + (size_t)2 * S * max_level_cells);  // [S][3][side]
+    unsigned* wrap_tab = reinterpret_cast<unsigned*>(sh_cd + (size_t)2 * S * max_level_cells);  // [2][S][3][side]
     const int N = p.N;
     // CTA -> (part of the sweep, group of S sources), part-major: the parts of one source have identical work and
     // would run in lock-step if they were co-resident; CTAs of different sources drift apart, so that one CTA's
@@ -382,7 +388,7 @@ sweep_smem_kernel(const int4* __restrict__ plan, const unsigned* __restrict__ dw
     const int ngroups = gridDim.x / parts;
     const int part = blockIdx.x / ngroups;
     const int first = (blockIdx.x - part * ngroups) * S;
-    int* level_start = reinterpret_cast<int*>(wrap_tab + (size_t)3 * S * side);  // [nlevels + 1], shared memory
+    int* level_start = reinterpret_cast<int*>(wrap_tab + (size_t)2 * 3 * S * side);  // [nlevels + 1], shared memory
     for (int t = threadIdx.x; t <= nlevels; t += BLOCK) level_start[t] = __ldg(level_start_all + part * (nlevels + 1) + t);
 
     for (int t = threadIdx.x; t < 256 * REP; t += BLOCK) log2_all[t] = __ldg(p.log2_tab + t / REP);
@@ -407,8 +413,12 @@ sweep_smem_kernel(const int4* __restrict__ plan, const unsigned* __restrict__ dw
         for (int t = threadIdx.x; t < 3 * side; t += BLOCK) {
             const int axis = t / side, d = t - axis * side + lo;
             const int c0 = axis == 0 ? i0[s] : (axis == 1 ? j0[s] : k0[s]);
-            const unsigned stride = axis == 0 ? (unsigned)N * N : (axis == 1 ? (unsigned)N : 1u);
-            wrap_tab[3 * s * side + t] = (unsigned)wrap(c0 + d, N) * stride;
+            const unsigned NN = (unsigned)N * N, w = (unsigned)wrap(c0 + d, N);
+            const unsigned stride = axis == 0 ? NN : (axis == 1 ? (unsigned)N : 1u);
+            // (k,i,j) order: i*N + j + k*N*N, behind the (i,j,k) grid
+            const unsigned stride_t = axis == 0 ? (unsigned)N : (axis == 1 ? 1u : NN);
+            wrap_tab[3 * s * side + t] = w * stride;
+            if (ZF) wrap_tab[3 * S * side + 3 * s * side + t] = w * stride_t + (axis == 0 ? p.zface_offset : 0u);
         }
     __syncthreads();
 
@@ -419,10 +429,10 @@ sweep_smem_kernel(const int4* __restrict__ plan, const unsigned* __restrict__ dw
         double* cur = sh_cd + (size_t)(m & 1) * S * max_level_cells;
         const double* prev = sh_cd + (size_t)((m & 1) ^ 1) * S * max_level_cells;
         if (m < 2)
-            sweep_level<S, BLOCK, REP, true, CDOUT, TEX, PF, HEAT>(plan, dwords, ncells, beg, end, m, cur, prev, max_level_cells,
+            sweep_level<S, BLOCK, REP, true, CDOUT, TEX, PF, HEAT, ZF>(plan, dwords, ncells, beg, end, m, cur, prev, max_level_cells,
                                                              wrap_tab, side, sk, live, p, log2_tab);
         else
-            sweep_level<S, BLOCK, REP, false, CDOUT, TEX, PF, HEAT>(plan, dwords, ncells, beg, end, m, cur, prev, max_level_cells,
+            sweep_level<S, BLOCK, REP, false, CDOUT, TEX, PF, HEAT, ZF>(plan, dwords, ncells, beg, end, m, cur, prev, max_level_cells,
                                                               wrap_tab, side, sk, live, p, log2_tab);
         __syncthreads();
         beg = end;
@@ -433,15 +443,15 @@ sweep_smem_kernel(const int4* __restrict__ plan, const unsigned* __restrict__ dw
 size_t sweep_smem_bytes(const SweepPlan& plan, int S, int rep)
 {
     return (size_t)256 * rep * sizeof(double2) + (size_t)2 * S * plan.max_level_cells * sizeof(double) +
-           (size_t)3 * S * plan.side * sizeof(unsigned) + (size_t)(plan.nlevels + 1) * sizeof(int);
+           (size_t)2 * 3 * S * plan.side * sizeof(unsigned) + (size_t)(plan.nlevels + 1) * sizeof(int);
 }
 
-template <int S, int BLOCK, int MINB, int REP, bool CDOUT, bool TEX, bool PF, bool HEAT = false>
+template <int S, int BLOCK, int MINB, int REP, bool CDOUT, bool TEX, bool PF, bool HEAT = false, bool ZF = false>
 static cudaError_t launch_smem_t(const SweepPlan& plan, const SweepParams& p, cudaStream_t stream)
 {
     const size_t smem = sweep_smem_bytes(plan, S, REP);
     const int grid = ((p.src_count + S - 1) / S) * plan.parts;
-    auto kernel = sweep_smem_kernel<S, BLOCK, MINB, REP, CDOUT, TEX, PF, HEAT>;
+    auto kernel = sweep_smem_kernel<S, BLOCK, MINB, REP, CDOUT, TEX, PF, HEAT, ZF>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kernel<<<grid, BLOCK, smem, stream>>>(plan.d_cells, plan.d_dwords, (int)plan.ncells, plan.d_level_start, plan.nlevels,
@@ -453,6 +463,15 @@ template <int S, int BLOCK, int MINB>
 static cudaError_t launch_smem_opts(const SweepPlan& plan, const SweepParams& p, int opts, cudaStream_t stream)
 {
     if (p.coldens_out) return launch_smem_t<S, BLOCK, MINB, 1, true, false, false>(plan, p, stream);  // debug path
+    if (p.zface_offset) {  // z-face cells through the (k,i,j)-ordered copies: the one-CTA-per-SM shapes only
+        if constexpr (S == 1 && BLOCK >= 768) {
+            if (p.phi_heat) return launch_smem_t<S, BLOCK, MINB, 1, false, true, true, true, true>(plan, p, stream);
+            return (opts & 1) ? launch_smem_t<S, BLOCK, MINB, 8, false, true, true, false, true>(plan, p, stream)
+                              : launch_smem_t<S, BLOCK, MINB, 1, false, true, true, false, true>(plan, p, stream);
+        } else {
+            return cudaErrorInvalidValue;
+        }
+    }
     if (p.phi_heat) return launch_smem_t<S, BLOCK, MINB, 1, false, true, false, true>(plan, p, stream);  // with heating
     switch (opts & 7) {
         case 0: return launch_smem_t<S, BLOCK, MINB, 1, false, false, false>(plan, p, stream);
@@ -754,6 +773,71 @@ cudaError_t launch_finish_phi(double* phi, const double* ntau, const double* kee
     int64_t blocks = (ncell + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     finish_phi_kernel<<<(int)blocks, 256, 0, stream>>>(phi, ntau, keep, ncell);
+    return cudaGetLastError();
+}
+
+// The opacity grid and its (k,i,j)-ordered copy ntau_t[k*N*N + i*N + j] through a 32x32 shared-memory tile, so that both
+// are written with coalesced stores.
+__global__ void prepare_nhi_transposed_kernel(const double* __restrict__ ndens, const double* __restrict__ xh_av,
+                                              double* __restrict__ ntau, double* __restrict__ ntau_t, double sig_dr, int N)
+{
+    __shared__ double tile[32][33];
+    const int i = blockIdx.z;
+    const int j0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int j = j0 + r, k = k0 + threadIdx.x;
+        if (j < N && k < N) {
+            const size_t idx = ((size_t)i * N + j) * N + k;
+            const double v = (ndens[idx] * (1.0 - xh_av[idx])) * sig_dr;
+            ntau[idx] = v;
+            tile[r][threadIdx.x] = v;
+        }
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int k = k0 + r, j = j0 + threadIdx.x;
+        if (j < N && k < N) ntau_t[((size_t)k * N + i) * N + j] = tile[threadIdx.x][r];
+    }
+}
+
+cudaError_t launch_prepare_nhi_transposed(const double* ndens, const double* xh_av, double* ntau, double* ntau_t, double sig_dr,
+                                          int N, cudaStream_t stream)
+{
+    dim3 grid((N + 31) / 32, (N + 31) / 32, N), block(32, 8);
+    prepare_nhi_transposed_kernel<<<grid, block, 0, stream>>>(ndens, xh_av, ntau, ntau_t, sig_dr, N);
+    return cudaGetLastError();
+}
+
+// finish_phi_kernel for a sweep that accumulated its z-face cells in the (k,i,j)-ordered copy phi_t:
+// phi[i][j][k] = (phi[i][j][k] + phi_t[k][i][j]) / ntau[i][j][k] (+ keep).
+__global__ void finish_phi_transposed_kernel(double* __restrict__ phi, const double* __restrict__ phi_t,
+                                             const double* __restrict__ ntau, const double* __restrict__ keep, int N)
+{
+    __shared__ double tile[32][33];
+    const int i = blockIdx.z;
+    const int j0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int k = k0 + r, j = j0 + threadIdx.x;
+        if (j < N && k < N) tile[r][threadIdx.x] = phi_t[((size_t)k * N + i) * N + j];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int j = j0 + r, k = k0 + threadIdx.x;
+        if (j < N && k < N) {
+            const size_t idx = ((size_t)i * N + j) * N + k;
+            const double sum = phi[idx] + tile[threadIdx.x][r];
+            double v = (sum != 0.0) ? sum / ntau[idx] : 0.0;
+            if (keep) v += keep[idx];
+            phi[idx] = v;
+        }
+    }
+}
+
+cudaError_t launch_finish_phi_transposed(double* phi, const double* phi_t, const double* ntau, const double* keep, int N,
+                                         cudaStream_t stream)
+{
+    dim3 grid((N + 31) / 32, (N + 31) / 32, N), block(32, 8);
+    finish_phi_transposed_kernel<<<grid, block, 0, stream>>>(phi, phi_t, ntau, keep, N);
     return cudaGetLastError();
 }
 

@@ -221,6 +221,7 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_o
                         pc.inv_np = 1.0 / ((double)n * pc.path);
                         if (c == 1 && (a == 1 || b == 1)) pc.flags |= (a == 1 && b == 1) ? PC_DIAG3 : PC_DIAG2;
                         if (owned && rated(i, j, k)) pc.flags |= PC_RATED;
+                        if (ka == m && ja < m && ia < m) pc.flags |= PC_ZFACE;
                         // upstream slots; zero-weight corners may fall outside the part -> slot 0, weight 0
                         const double s[4] = {pc.wA * pc.wB, pc.wB * (1.0 - pc.wA), pc.wA * (1.0 - pc.wB),
                                              (1.0 - pc.wA) * (1.0 - pc.wB)};

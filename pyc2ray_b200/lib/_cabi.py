@@ -49,6 +49,7 @@ SIGNATURES = {
     "asora_set_sphere_only": (_i, [_i]),
     "asora_last_sweep_stats": (_i, [ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i64),
                                     ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_float)]),
+    "asora_last_sweep_kernel_ms": (_i, [ctypes.POINTER(ctypes.c_float)]),
     "asora_cells_per_source": (_i64, [_i, _d]),
     "asora_last_error": (ctypes.c_char_p, []),
     "asora_version": (ctypes.c_char_p, []),

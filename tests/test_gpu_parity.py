@@ -387,6 +387,24 @@ def test_bench_radius_launch_shape_vs_oracle(libs):
             _cabi.check(_cabi.L.asora_set_tuning(1, block))
             alt, _, _ = _sweep(libasora, _cabi, c, 0)
             _assert_close(alt, ref, f"R=30, {block} threads")
+        # z-face cells through the (k,i,j)-ordered copies of the opacity and rate grids (automatic only for sweeps of
+        # 5e8 updates and more; bit 19 of the tuning word forces it), also on top of earlier rates and sphere-only
+        for block in (896, 1024):
+            _cabi.check(_cabi.L.asora_set_tuning(1, block | (8 << 16)))
+            alt, _, _ = _sweep(libasora, _cabi, c, 0)
+            _assert_close(alt, ref, f"R=30, {block} threads, transposed z faces")
+        _cabi.check(_cabi.L.asora_set_sphere_only(1))
+        alt, _, _ = _sweep(libasora, _cabi, c, 0)
+        _cabi.check(_cabi.L.asora_set_sphere_only(0))
+        _assert_close(alt, ref, "R=30, transposed z faces, sphere only")
+        _cabi.check(_cabi.L.asora_buffer_upload(_cabi.BUF_XH_AV, _cabi.dptr(np.ascontiguousarray(xh.ravel()))))
+        h = ns // 2
+        args = (c["sig"], c["dr"])
+        _cabi.check(_cabi.L.asora_raytrace_device(R, *args, 0, h, -20.0, dlogtau, thin.size, 1))
+        _cabi.check(_cabi.L.asora_raytrace_device(R, *args, h, ns - h, -20.0, dlogtau, thin.size, 0))
+        acc = np.empty(N ** 3)
+        _cabi.check(_cabi.L.asora_buffer_download(_cabi.BUF_PHI_ION, _cabi.dptr(acc)))
+        _assert_close(acc, ref, "R=30, transposed z faces, two accumulating sweeps")
     finally:
         _cabi.L.asora_set_tuning(0, 0)
         libasora.device_close()

@@ -113,7 +113,7 @@ def _close(a, b, rtol, what):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,variant,tuning", [
     ("multi_n32", 1, None), ("multi_n32", 1, (2, 256)), ("multi_n32", 2, None), ("bench_like_n32", 1, None),
-    ("mid_n48_r14", 1, (1, 896)), ("clip_full_n24", 2, None), ("thin_n24", 1, None)])
+    ("mid_n48_r14", 1, (1, 896)), ("mid_n48_r14", 1, (1, 896 | (8 << 16))), ("clip_full_n24", 2, None), ("thin_n24", 1, None)])
 def test_gpu_heating_vs_oracle(name, variant, tuning):
     c = heat_case(name)
     phi, heat, phi2 = _gpu_heat(c, variant, tuning)
