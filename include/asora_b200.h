@@ -169,8 +169,10 @@ int asora_debug_single_source(double R, double sig, double dr, const double* xh_
                               double minlogtau, double dlogtau, int NumTau, double* coldensh_out,
                               double* phi_ion);
 
-/* Force the sweep variant: 0 = automatic, 1 = shared-memory level sweep (one CTA per source batch),
- * 2 = grid-cooperative level sweep (whole GPU per source).  Returns non-zero for unknown values. */
+/* Force the sweep variant: 0 = automatic, 1 = shared-memory level sweep (one CTA per source batch, one cell per
+ * thread), 2 = grid-cooperative level sweep (whole GPU per source), 3 = mirror-image sweep (one plan entry and up to
+ * eight octant images per thread; needs a mirror-symmetric cell set, i.e. q_max <= N/2 - 1 on even meshes).
+ * Returns non-zero for unknown values. */
 int asora_set_sweep_variant(int variant);
 
 /* Sphere-only sweeps.  The reference visits the whole octahedron(q_max) & cube although only cells inside
@@ -188,6 +190,26 @@ int asora_set_sphere_only(int sphere_only);
  * bit 19 toggles the (k,i,j)-ordered grid copies for z-face cells (automatic only for sweeps of >= 5e8 updates);
  * bits 20-23 force the number of parts a source is split into (1, 2, 4, 8).  For tuning and profiling. */
 int asora_set_tuning(int sources_per_cta, int block_threads);
+
+/* Override the launch shape of the mirror-image sweep (variant 3): octants per CTA (8, 4, 2), mirror images per thread,
+ * images evaluated side by side, threads per CTA; 0 = automatic for that field.  Only instantiated combinations are
+ * accepted at launch time (csrc/sweep_octant.cu).  For tuning and profiling. */
+int asora_set_octant_shape(int octants_per_cta, int images_per_thread, int batch, int block_threads);
+
+/* Number of sweep plans built since the library was loaded (the plans are cached per mesh, radius, cell size and
+ * split; tests use this to check that repeated sweeps do not rebuild them). */
+int asora_plan_builds(void);
+
+/* The host-side sweep plan exactly as the kernels consume it (csrc/sweep_plan.cu); needs no device.  octant != 0: the
+ * positive-octant plan of the mirror-image sweep (parts ignored), else the whole-sweep plan split into `parts`.
+ * Returns the number of plan entries (or -1); info[6] = {levels, largest level, lowest offset, offsets per axis,
+ * q_max, parts}.  The arrays are filled only when capacity >= the number of entries: path[n], inv_np[n],
+ * upstream_slots[4n], offsets[3n] (biased by -info[2]; octant plans: absolute values), flags[n] (octant plans:
+ * flags >> 5 = mask of zero offsets), minor_ab[2n], level_start[parts * (levels + 1)], level_mid[3 * levels]
+ * (octant plans only).  Any pointer may be NULL.  For tests of the plan construction. */
+int64_t asora_plan_export(int N, double R, double dr, int sphere_only, int octant, int parts, int64_t capacity,
+                          double* path, double* inv_np, uint16_t* upstream_slots, uint8_t* offsets, uint8_t* flags,
+                          uint8_t* minor_ab, int* level_start, int* level_mid, int* info);
 
 /* Statistics of the most recent ray trace: variant used, number of kernel launches, number of
  * (source, cell) updates, q_max, number of Chebyshev levels, device milliseconds (CUDA events on

@@ -56,7 +56,15 @@ struct Context {
     int* src_pos_sorted = nullptr;   // the same sources in Morton order of their cells: consecutive CTAs
     double* src_flux_sorted = nullptr;  // then sweep neighbouring regions and share ndens/phi lines in L2
     int nsrc = 0;
-    SweepPlan plan;
+    // sweep plans, most recently used first: (N, R, dr, sphere_only, kind, parts) -> plan.  A time step alternates between
+    // at most a few of them (full / sphere-only, split or not), and a rebuild costs several O(side^3) host passes plus a
+    // synchronous upload, so the cache holds more than one and remembers the automatic split per key.
+    static constexpr int kPlanCache = 6;
+    SweepPlan plans[kPlanCache];
+    int plan_failed_parts[kPlanCache] = {0};
+    struct AutoParts { int N; double R, dr; bool sphere_only; int parts; };
+    std::vector<AutoParts> auto_parts;   // parts chosen by the automatic split, per (N, R, dr, sphere_only)
+    int plan_builds = 0;                 // number of plans built so far (tests: the cache must hit)
     // temperature factors of the chemistry (chemistry.cu), valid for the TEMP buffer contents and constants below
     double2* chem_factors = nullptr;
     bool chem_factors_valid = false;
@@ -70,8 +78,10 @@ struct Context {
     int64_t chem_stage_n = 0;
     // stats of the last sweep
     int variant_forced = 0;
+    bool auto_octant = false;  // automatic selection may pick the mirror-image sweep
     int tune_S = 0, tune_block = 0, tune_opts = 0;
     int tune_parts = 0;
+    int oct_noct = 0, oct_opt = 0, oct_batch = 0, oct_block = 0;  // forced shape of the mirror-image sweep (0 = automatic)
     int slab_begin = 0, slab_count = 0;  // active planes of a slab-decomposed run (0 = whole grid)
     int sphere_only = 0;
     // parameters of the last sweep, for the lazily evaluated update count; and a one-entry cache of it
@@ -239,6 +249,26 @@ int ensure_chem_factors(double bh00, double albpow, double colh0, double temph0)
     return 0;
 }
 
+// Cached sweep plan for the current mesh: octant = true -> build_octant_plan, else build_sweep_plan(parts).
+// Returns nullptr (and sets err) when the plan cannot be built.
+SweepPlan* get_plan(int N, double R, double dr, bool sphere_only, bool octant, int parts, std::string& err)
+{
+    SweepPlan* c = g.plans;
+    for (int i = 0; i < Context::kPlanCache; i++) {
+        if (c[i].valid && c[i].N == N && c[i].R == R && c[i].dr == dr && c[i].sphere_only == sphere_only &&
+            c[i].octant == octant && c[i].parts == parts) {
+            std::rotate(c, c + i, c + i + 1);  // most recently used first
+            return &c[0];
+        }
+    }
+    free_sweep_plan(c[Context::kPlanCache - 1]);  // evict the least recently used entry
+    std::rotate(c, c + Context::kPlanCache - 1, c + Context::kPlanCache);
+    g.plan_builds++;
+    const bool ok = octant ? build_octant_plan(c[0], N, R, dr, sphere_only, err)
+                           : build_sweep_plan(c[0], N, R, dr, sphere_only, parts, err);
+    return ok ? &c[0] : nullptr;
+}
+
 // Choose and launch the sweep for sources [begin, begin+count).  Inputs already on the device.
 int run_sweep(double R, double sig, double dr, int begin, int count, double minlogtau, double dlogtau,
               int NumTau, bool zero_phi, double* coldens_grid)
@@ -323,53 +353,100 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     g.last_updates = -1;
     g.last_ms = 0.f;
 
-    // Variant selection: the shared-memory sweep needs two levels of column densities per source.
+    // Variant selection.  1: shared-memory level sweep, one cell per thread (sweep_kernels.cu); 3: mirror-image sweep,
+    // one plan entry and up to eight octant images per thread (sweep_octant.cu), for mirror-symmetric cell sets;
+    // 2: grid-cooperative sweep through L2 scratch grids when a level does not fit in shared memory.
     int variant = g.variant_forced;
     int S = 1, block = 256, opts = 0;
-    bool plan_ok = false;
-    if (variant != 2) {
-        const int lo_side = 2 * std::min(p.q_max, std::max(-p.last_l, p.last_r)) + 1;
+    int noct = 8, opt = 8, batch = 4;
+    SweepPlan* plan = nullptr;
+    const int hi_cells = std::min(p.q_max, std::max(-p.last_l, p.last_r));
+    const bool symmetric = std::min(p.q_max, p.last_r) == std::min(p.q_max, -p.last_l) && hi_cells <= 126;
+    const size_t budget = (size_t)g.smem_optin;
+    if ((variant == 3 || (variant == 0 && g.auto_octant)) && symmetric && !coldens_grid) {
+        std::string err;
+        plan = get_plan(N, R, dr, sphere_only, true, 1, err);
+        if (!plan && variant == 3) return fail(err);
+        if (plan) {
+            // octants per CTA: all eight while their level buffers fit, else half-spaces / quadrants as separate CTAs
+            noct = g.oct_noct > 0 ? g.oct_noct : 8;
+            while (g.oct_noct == 0 && noct > 2 && sweep_octant_smem_bytes(*plan, noct, 1, false) > budget) noct /= 2;
+            if (sweep_octant_smem_bytes(*plan, noct, 1, false) > budget) {
+                if (variant == 3) return fail("sweep variant 3 forced but a level does not fit in shared memory");
+                plan = nullptr;
+            }
+        }
+        if (plan) {
+            // Launch shape (measured on B200, scripts/octant_probe.py): see DESIGN.md, "Mirror-image sweep"
+            const int maxc = plan->max_level_cells;
+            if (noct == 8) {
+                if (maxc >= 512) { opt = 8; batch = 4; block = 384; }
+                else if (maxc >= 128) { opt = 4; batch = 2; block = 256; }
+                else { opt = 8; batch = 2; block = 64; }
+            } else if (noct == 4) {
+                opt = 4; batch = 4; block = 256;
+            } else {
+                opt = 2; batch = 2; block = 256;
+            }
+            if (g.oct_opt > 0) opt = g.oct_opt;
+            if (g.oct_batch > 0) batch = g.oct_batch;
+            if (g.oct_block > 0) block = g.oct_block;
+            if (!sweep_octant_shape_ok(noct, opt, batch, block)) return fail("mirror-image sweep: launch shape not instantiated");
+            opts = g.tune_opts & 9;  // profiling knobs: bit 0 log2-table copies, bit 3 no de-duplication of plane cells
+            variant = 3;
+        }
+    }
+    if (variant == 3 && !plan) return fail("sweep variant 3 forced but the swept region is not mirror-symmetric");
+    if (variant != 2 && variant != 3) {
+        const int lo_side = 2 * hi_cells + 1;
         if (p.q_max <= 127 && lo_side <= 255) {
             // Parts: start from the whole sweep and split (half-spaces, quadrants, octants) only until one
             // source's two level buffers fit in shared memory.  (Measured at R = 30, 256^3: 1 part x 1024
             // threads 20.6 ms, 2 x 512: 21.4, 4 x 256: 21.2, 8 x 256 with two sources: 21.1 -- splitting does
-            // not pay by itself, it extends the shared-memory variant to radii of ~65 cells.)
+            // not pay by itself, it extends the shared-memory variant to radii of ~65 cells.)  The split found for a
+            // (mesh, radius, cell size) is remembered, so that later sweeps go straight to the cached plan.
             int parts = g.tune_parts > 0 ? g.tune_parts : 1;
+            Context::AutoParts* memo = nullptr;
+            if (g.tune_parts == 0) {
+                for (auto& a : g.auto_parts)
+                    if (a.N == N && a.R == R && a.dr == dr && a.sphere_only == sphere_only) memo = &a;
+                if (memo) parts = memo->parts;
+            }
             for (;;) {
-                if (!(g.plan.valid && g.plan.N == N && g.plan.R == R && g.plan.dr == dr &&
-                      g.plan.sphere_only == sphere_only && g.plan.parts == parts)) {
-                    std::string err;
-                    if (!build_sweep_plan(g.plan, N, R, dr, sphere_only, parts, err)) {
-                        if (variant == 1) return fail(err);
-                        break;
-                    }
+                std::string err;
+                plan = get_plan(N, R, dr, sphere_only, false, parts, err);
+                if (!plan) {
+                    if (variant == 1) return fail(err);
+                    break;
                 }
                 if (g.tune_parts > 0 || parts == 8) break;
-                if (sweep_smem_bytes(g.plan, 1, 1) <= (size_t)g.smem_optin) break;
+                if (sweep_smem_bytes(*plan, 1, 1) <= budget) break;
                 parts *= 2;
             }
-            plan_ok = g.plan.valid;
+            if (plan && g.tune_parts == 0 && !memo) {
+                if (g.auto_parts.size() >= 16) g.auto_parts.erase(g.auto_parts.begin());
+                g.auto_parts.push_back({N, R, dr, sphere_only, plan->parts});
+            }
         }
-        if (plan_ok) {
-            const size_t per_src = sweep_smem_bytes(g.plan, 1, 1);
-            const size_t budget = (size_t)g.smem_optin;
+        if (plan) {
+            const size_t per_src = sweep_smem_bytes(*plan, 1, 1);
             if (per_src > budget) {
-                plan_ok = false;
+                plan = nullptr;
             } else {
                 // Launch shape (measured on B200, scripts/perf_probe4.py): 256 threads while a level is at
                 // most a few passes wide, 512 for wider levels when two CTAs fit per SM, 1024 when only one
                 // does; two sources per CTA (plan decode and barriers amortised) when both fit next to >= 3
                 // resident CTAs.
-                const int maxc = g.plan.max_level_cells;
+                const int maxc = plan->max_level_cells;
                 // (one CTA per SM: 896 threads at 72 registers beat 1024 at 64, where ptxas spills and delays
                 // loads, and 768 / 640 / 512 threads: 17.7 vs 18.3 / 17.8 / 18.6 / 20.5 ms at R = 30)
                 block = maxc < 2048 ? 256 : (2 * per_src <= budget ? 512 : 896);
-                S = (block == 256 && count >= 8 * g.sm_count && 3 * sweep_smem_bytes(g.plan, 2, 1) <= budget) ? 2 : 1;
+                S = (block == 256 && count >= 8 * g.sm_count && 3 * sweep_smem_bytes(*plan, 2, 1) <= budget) ? 2 : 1;
                 if (g.tune_S > 0 && (size_t)g.tune_S * per_src <= budget) S = g.tune_S;
                 if (g.tune_block > 0) block = g.tune_block;
                 // eight bank-staggered copies of the log2 table (28 KB more) for the long-lived one-per-SM CTAs of large
                 // radii; short sweeps do not recover the cost of filling them (R = 10.76: 1.20 vs 1.13 ms)
-                opts = (block > 512 && sweep_smem_bytes(g.plan, S, 8) <= budget) ? 1 : 0;
+                opts = (block > 512 && sweep_smem_bytes(*plan, S, 8) <= budget) ? 1 : 0;
                 // table gathers through the texture pipe: always (R = 30: 18.9 -> 18.2 ms; R = 10.76: 1.25 -> 1.21 ms);
                 // offsets word one cell ahead: only the small-radius shape gains (R = 10.76, two sources x 256
                 // threads: 1.21 -> 1.11 ms; R = 30, 1024 threads: 18.2 -> 18.9 ms) -- scripts/perf_probe6.py
@@ -378,9 +455,9 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
                 opts ^= (g.tune_opts & 7);  // profiling knob: bits 16-18 of set_tuning's block_threads toggle the options
             }
         }
-        if (variant == 1 && !plan_ok) return fail("sweep variant 1 forced but a level does not fit in shared memory");
+        if (variant == 1 && !plan) return fail("sweep variant 1 forced but a level does not fit in shared memory");
+        if (variant == 0) variant = plan ? 1 : 2;
     }
-    if (variant == 0) variant = plan_ok ? 1 : 2;
 
     // host-side preparation of the grid-cooperative sweep (kept outside the timed region)
     int groups = 1;
@@ -412,9 +489,13 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     // (R = 30: 17.5 -> 16.4 ms with two extra transposing passes of 0.1 ms each).  Not for short sweeps, which would not
     // recover the passes, nor for slab-decomposed runs, whose plane ranges are not contiguous in the copies.
     const bool slab_active = g.slab_count > 0 && g.slab_count < N;
-    bool use_z = variant == 1 && S == 1 && block >= 768 && g.zface_ok && !coldens_grid && !slab_active && g.plan.nlevels >= 24 &&
-                 (double)count * (double)(g.plan.ncells / g.plan.parts) >= 5e8;
-    if (g.tune_opts & 8) use_z = !use_z && variant == 1 && S == 1 && block >= 768 && g.zface_ok && !coldens_grid && !slab_active;  // profiling knob
+    const bool z_shape = (variant == 1 && S == 1 && block >= 768) || (variant == 3 && noct * plan->max_level_cells >= 2048 && !p.phi_heat &&
+                                                                         sweep_octant_shape_ok(noct, opt, batch, block) == 2);
+    const bool z_possible = z_shape && g.zface_ok && !coldens_grid && !slab_active;
+    bool use_z = z_possible && plan->nlevels >= 24 &&
+                 (double)count * (double)(plan->ncells / plan->parts) * (variant == 3 ? 8.0 : 1.0) >= 5e8;
+    if (g.tune_opts & 8 && variant == 1) use_z = !use_z && z_possible;  // profiling knob
+    if (g.tune_opts & 2 && variant == 3) use_z = !use_z && z_possible;  // profiling knob (mirror-image sweep)
     p.zface_offset = use_z ? (unsigned)g.ncell : 0u;
 
     // timed region (asora_last_sweep_stats: kernel_ms): nHI pre-pass, rate-grid zeroing, sweep
@@ -458,9 +539,14 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
 
     CK(cudaEventRecord(g.evk0, g.stream));
     if (variant == 1) {
-        g.last_levels = g.plan.nlevels;
-        cudaError_t e = launch_sweep_smem(g.plan, p, S, block, opts, g.stream, &g.last_launches);
+        g.last_levels = plan->nlevels;
+        cudaError_t e = launch_sweep_smem(*plan, p, S, block, opts, g.stream, &g.last_launches);
         if (e != cudaSuccess) return fail_cuda("sweep_smem_kernel launch", e);
+    } else if (variant == 3) {
+        g.last_levels = plan->nlevels;
+        if (p.zface_offset && sweep_octant_smem_bytes(*plan, noct, (opts & 1) ? 8 : 1, true) > budget) opts &= ~1;
+        cudaError_t e = launch_sweep_octant(*plan, p, noct, opt, batch, block, opts, g.stream, &g.last_launches);
+        if (e != cudaSuccess) return fail_cuda("sweep_octant_kernel launch", e);
     } else {
         cudaError_t e = launch_sweep_grid(p, groups, g.grid_counters, g.stream, &g.last_launches, &g.last_levels);
         if (e != cudaSuccess) return fail_cuda("sweep_grid_kernel launch", e);
@@ -619,7 +705,8 @@ int asora_device_close(void)
     g.chem_partials = nullptr;
     g.chem_iparts = nullptr;
     g.ntab = g.nsrc = 0;
-    free_sweep_plan(g.plan);
+    for (int i = 0; i < Context::kPlanCache; i++) free_sweep_plan(g.plans[i]);
+    g.auto_parts.clear();
     if (g.ev0) cudaEventDestroy(g.ev0);
     if (g.ev1) cudaEventDestroy(g.ev1);
     if (g.evk0) cudaEventDestroy(g.evk0);
@@ -1003,9 +1090,64 @@ int asora_global_pass(double dt, const double* ndens, const double* temp, const 
 
 int asora_set_sweep_variant(int variant)
 {
-    if (variant < 0 || variant > 2) return fail("set_sweep_variant: unknown variant");
+    if (variant < 0 || variant > 3) return fail("set_sweep_variant: unknown variant");
     g.variant_forced = variant;
     return 0;
+}
+
+int asora_set_octant_shape(int octants_per_cta, int images_per_thread, int batch, int block_threads)
+{
+    if (octants_per_cta != 0 || images_per_thread != 0 || batch != 0 || block_threads != 0) {
+        const int no = octants_per_cta ? octants_per_cta : 8;
+        if (!(no == 8 || no == 4 || no == 2)) return fail("set_octant_shape: octants per CTA must be 8, 4 or 2");
+    }
+    g.oct_noct = octants_per_cta;
+    g.oct_opt = images_per_thread;
+    g.oct_batch = batch;
+    g.oct_block = block_threads;
+    return 0;
+}
+
+int asora_plan_builds(void) { return g.plan_builds; }
+
+int64_t asora_plan_export(int N, double R, double dr, int sphere_only, int octant, int parts, int64_t capacity,
+                          double* path, double* inv_np, uint16_t* upstream_slots, uint8_t* offsets, uint8_t* flags,
+                          uint8_t* minor_ab, int* level_start, int* level_mid, int* info)
+{
+    SweepPlan plan;
+    std::string err;
+    const bool ok = octant ? build_octant_plan(plan, N, R, dr, sphere_only != 0, err, false)
+                           : build_sweep_plan(plan, N, R, dr, sphere_only != 0, parts, err, false);
+    if (!ok) {
+        fail(err);
+        return -1;
+    }
+    const int64_t n = (int64_t)plan.cells.size();
+    if (info) {
+        info[0] = plan.nlevels;
+        info[1] = plan.max_level_cells;
+        info[2] = plan.lo;
+        info[3] = plan.side;
+        info[4] = plan.q_max;
+        info[5] = plan.parts;
+    }
+    if (capacity >= n) {
+        for (int64_t e = 0; e < n; e++) {
+            const PlanCell& c = plan.cells[e];
+            if (path) path[e] = c.path;
+            if (inv_np) inv_np[e] = c.inv_np;
+            if (upstream_slots) for (int t = 0; t < 4; t++) upstream_slots[4 * e + t] = c.nb[t];
+            if (offsets) for (int t = 0; t < 3; t++) offsets[3 * e + t] = c.d[t];
+            if (flags) flags[e] = c.flags;
+            if (minor_ab) {
+                minor_ab[2 * e] = (uint8_t)(c.ab & 0xff);
+                minor_ab[2 * e + 1] = (uint8_t)((c.ab >> 8) & 0xff);
+            }
+        }
+        if (level_start) std::copy(plan.level_start.begin(), plan.level_start.end(), level_start);
+        if (level_mid) std::copy(plan.level_mid.begin(), plan.level_mid.end(), level_mid);
+    }
+    return n;
 }
 
 int asora_set_sphere_only(int sphere_only)

@@ -56,8 +56,10 @@ struct SweepPlan {
     int lo = 0, side = 0;              // offsets span [lo, lo+side) on every axis
     bool sphere_only = false;          // unrated cells left out (asora_set_sphere_only)
     int parts = 1;                     // independent pieces per source (sweep_plan.cu), one CTA each
+    bool octant = false;               // octant plan: positive octant only, applied to its mirror images (build_octant_plan)
     int64_t ncells = 0;                // plan entries (all parts; bounding planes appear once per part)
     std::vector<int> level_start;      // [parts][nlevels+1], absolute entry offsets
+    std::vector<int> level_mid;        // octant plans: [3][nlevels] class A / class B boundary for OPT = 8, 4, 2 (sweep_plan.cu)
     std::vector<PlanCell> cells;       // level-major, lexicographic (di,dj,dk) inside a level
     // device copy, split into two 16-byte streams (structure of arrays): a warp's LDG.128 then covers 4
     // contiguous 128-byte lines instead of the lines of a strided array of structures -- the L1/LSU
@@ -126,14 +128,24 @@ __device__ __forceinline__ double fast_div(double a, double b)
 // host-side helpers implemented in sweep_plan.cu
 int asora_qmax(int N, double R);
 int64_t asora_count_cells(int N, double R);
-bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_only, int parts, std::string& err);
+// upload = false: host-side plan only (plan.cells, level_start, level_mid), no device needed
+bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_only, int parts, std::string& err,
+                      bool upload = true);
 int64_t asora_count_rated_cells(int N, double R, double dr);
+bool build_octant_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_only, std::string& err, bool upload = true);
 void free_sweep_plan(SweepPlan& plan);
 
 // launchers implemented in sweep_kernels.cu
 size_t sweep_smem_bytes(const SweepPlan& plan, int sources_per_cta, int log2_copies);
 cudaError_t launch_sweep_smem(const SweepPlan& plan, const SweepParams& p, int sources_per_cta, int block,
                               int opts, cudaStream_t stream, int* launches);
+// sweep_octant.cu: the mirror-image sweep.  `noct` octants per CTA (8, 4, 2: a source is split over 8/noct CTAs),
+// `opt` mirror images per thread of which `batch` are evaluated side by side, `block` threads; cudaErrorNotSupported
+// for combinations that are not instantiated (sweep_octant_shape_ok).
+size_t sweep_octant_smem_bytes(const SweepPlan& plan, int noct, int log2_copies, bool zface);
+cudaError_t launch_sweep_octant(const SweepPlan& plan, const SweepParams& p, int noct, int opt, int batch, int block, int opts,
+                                cudaStream_t stream, int* launches);
+int sweep_octant_shape_ok(int noct, int opt, int batch, int block);  // 0 no, 1 yes, 2 yes incl. z-face copies
 int sweep_grid_groups(const SweepParams& p, int max_groups, int* total_ctas_out, int* group_ctas_out);
 cudaError_t launch_sweep_grid(const SweepParams& p, int ngroups, unsigned* counters, cudaStream_t stream,
                               int* launches, int* levels);

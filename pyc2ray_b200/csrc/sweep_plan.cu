@@ -71,6 +71,38 @@ int64_t asora_count_rated_cells(int N, double R, double dr)
     return cnt;
 }
 
+// Device copy of plan.cells as two 16-byte streams + the 4-byte offsets stream, and the level bounds.
+static bool upload_plan(SweepPlan& plan, std::string& err)
+{
+    const int64_t total = (int64_t)plan.cells.size();
+    std::vector<int4> soa(2 * (size_t)total);
+    for (int64_t e = 0; e < total; e++) {
+        const int4* src = reinterpret_cast<const int4*>(&plan.cells[e]);
+        soa[e] = src[1];
+        soa[total + e] = src[2];
+    }
+    std::vector<unsigned> dwords((size_t)total);
+    for (int64_t e = 0; e < total; e++) dwords[e] = (unsigned)soa[total + e].z;
+    cudaError_t e = cudaMalloc(&plan.d_cells, sizeof(int4) * soa.size());
+    if (e == cudaSuccess) e = cudaMalloc(&plan.d_dwords, sizeof(unsigned) * dwords.size());
+    if (e == cudaSuccess)
+        e = cudaMemcpy(plan.d_dwords, dwords.data(), sizeof(unsigned) * dwords.size(), cudaMemcpyHostToDevice);
+    std::vector<int> bounds(plan.level_start);  // level bounds, then (octant plans) the class boundaries
+    bounds.insert(bounds.end(), plan.level_mid.begin(), plan.level_mid.end());
+    if (e == cudaSuccess) e = cudaMalloc(&plan.d_level_start, sizeof(int) * bounds.size());
+    if (e == cudaSuccess)
+        e = cudaMemcpy(plan.d_cells, soa.data(), sizeof(int4) * soa.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(plan.d_level_start, bounds.data(), sizeof(int) * bounds.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        err = std::string("sweep plan upload: ") + cudaGetErrorString(e);
+        free_sweep_plan(plan);
+        return false;
+    }
+    plan.valid = true;
+    return true;
+}
+
 // One sweep may be split into `parts` in {1,2,4,8} independent pieces by the signs of the offsets on z,
 // (y,z) or (x,y,z): every non-zero interpolation weight points one step towards the source, so a cell's
 // upstream cells have offsets of the same sign or zero, and a zero offset only ever pairs with the weight of
@@ -78,7 +110,7 @@ int64_t asora_count_rated_cells(int N, double R, double dr)
 // bounding planes (offset 0 on a constrained axis); the planes are recomputed by every part that touches
 // them but receive their rate from the all-positive side only ("owned" cells keep PC_RATED).  Parts of one
 // source run as separate CTAs with 1/parts of the shared memory each.
-bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_only, int parts, std::string& err)
+bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_only, int parts, std::string& err, bool upload)
 {
     free_sweep_plan(plan);
     if (!(parts == 1 || parts == 2 || parts == 4 || parts == 8)) {
@@ -244,7 +276,6 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_o
                     plan.cells[(size_t)ls[m] + slot[sidx(i, j, k)]] = pc;
                 }
     }
-    const int64_t total = (int64_t)plan.cells.size();
     plan.N = N;
     plan.R = R;
     plan.dr = dr;
@@ -255,33 +286,196 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_o
     plan.side = side;
     plan.sphere_only = sphere_only;
     plan.parts = parts;
-    plan.ncells = total;
+    plan.ncells = (int64_t)plan.cells.size();
 
-    std::vector<int4> soa(2 * (size_t)total);
-    for (int64_t e = 0; e < total; e++) {
-        const int4* src = reinterpret_cast<const int4*>(&plan.cells[e]);
-        soa[e] = src[1];
-        soa[total + e] = src[2];
-    }
-    std::vector<unsigned> dwords((size_t)total);
-    for (int64_t e = 0; e < total; e++) dwords[e] = (unsigned)soa[total + e].z;
-    cudaError_t e = cudaMalloc(&plan.d_cells, sizeof(int4) * soa.size());
-    if (e == cudaSuccess) e = cudaMalloc(&plan.d_dwords, sizeof(unsigned) * dwords.size());
-    if (e == cudaSuccess)
-        e = cudaMemcpy(plan.d_dwords, dwords.data(), sizeof(unsigned) * dwords.size(), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&plan.d_level_start, sizeof(int) * plan.level_start.size());
-    if (e == cudaSuccess)
-        e = cudaMemcpy(plan.d_cells, soa.data(), sizeof(int4) * soa.size(), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess)
-        e = cudaMemcpy(plan.d_level_start, plan.level_start.data(), sizeof(int) * plan.level_start.size(),
-                       cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
-        err = std::string("sweep plan upload: ") + cudaGetErrorString(e);
-        free_sweep_plan(plan);
+    plan.octant = false;
+    plan.level_mid.clear();
+    return upload ? upload_plan(plan, err) : true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Octant plan (sweep_octant.cu)
+// ---------------------------------------------------------------------------------------------------
+// Everything the plan tabulates is invariant under flipping the sign of any offset: the dominant-axis choice and its
+// tie order compare absolute values (raytracing.cu:394,446,491), the fractions, the path and the sphere test
+// (raytracing.cu:302-305: squares) depend on |di|, |dj|, |dk| only, and the upstream cells are one step towards the
+// source on every axis.  The octant plan therefore lists only the closed positive octant (di, dj, dk >= 0) of
+// octahedron(q_max) & cube, and the kernel applies every entry to its up to eight mirror images, which share the
+// entry's fetch, decode and interpolation weights.  The eight images keep separate level buffers with identical slot
+// numbering, so the upstream slots of an entry are the same numbers in every image.  A cell with a zero offset lies on
+// the plane between two images: it is evaluated once (by the image with a clear sign bit on that axis, which also owns
+// its rate) and stored into the buffers of all the images it borders; `flags >> 5` is the mask of zero offsets in the
+// octant-bit order (bit 2 = x, bit 1 = y, bit 0 = z).  Needs a mirror-symmetric cell set: -lo == hi on every axis
+// (always for odd N; for even N while q_max <= N/2 - 1).
+// Order inside a level: by zero mask in the order 0, 4, 2, 6, 1, 5, 3, 7 (bit 0 most significant), so that for a thread
+// that iterates the images of the low log2(OPT) bits itself the cells without a zero offset on those axes ("class A":
+// all OPT images distinct) form a prefix of the level and the plane cells it can de-duplicate ("class B") the rest;
+// plan.level_mid holds the three boundaries (OPT = 8, 4, 2).  Inside each zero-mask group rated cells come first
+// (whole warps skip the rate arithmetic of the octahedron's corners), then lexicographic order with k fastest.
+bool build_octant_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_only, std::string& err, bool upload)
+{
+    free_sweep_plan(plan);
+    const int Q = asora_qmax(N, R);
+    int ll, lr;
+    clip_bounds(N, ll, lr);
+    const int lo = std::max(ll, -Q), hi = std::min(lr, Q);
+    if (-lo != hi) {
+        err = "octant plan: the swept region is not mirror-symmetric (even mesh, q_max > N/2 - 1)";
         return false;
     }
-    plan.valid = true;
-    return true;
+    if (hi > 126) {
+        err = "octant plan: radius too large for byte-sized offsets";
+        return false;
+    }
+    const int side = hi + 1;  // offsets 0..hi
+    const double R2 = R * R;
+    auto rated = [&](int i, int j, int k) { return cell_rated(i, j, k, dr, R2); };
+    auto level_of = [](int i, int j, int k) { return std::max(i, std::max(j, k)); };
+    auto member = [&](int i, int j, int k) {
+        if (i + j + k > Q) return false;
+        return !sphere_only || rated(i, j, k);
+    };
+    auto zmask_of = [](int i, int j, int k) { return (i == 0 ? 4 : 0) | (j == 0 ? 2 : 0) | (k == 0 ? 1 : 0); };
+    int nlevels = hi + 1;
+    {
+        std::vector<char> used(nlevels, 0);
+        for (int i = 0; i <= hi; i++)
+            for (int j = 0; j <= hi; j++)
+                for (int k = 0; k <= hi; k++)
+                    if (member(i, j, k)) used[level_of(i, j, k)] = 1;
+        while (nlevels > 1 && !used[nlevels - 1]) nlevels--;
+    }
+    // group of a cell inside its level: 2 * bit-reversed zmask + (unrated)
+    auto group_of = [&](int i, int j, int k) {
+        const int z = zmask_of(i, j, k);
+        const int zr = ((z & 1) << 2) | (z & 2) | ((z >> 2) & 1);
+        return 2 * zr + (rated(i, j, k) ? 0 : 1);
+    };
+    std::vector<int> gcount((size_t)nlevels * 16, 0);
+    for (int i = 0; i <= hi; i++)
+        for (int j = 0; j <= hi; j++)
+            for (int k = 0; k <= hi; k++)
+                if (member(i, j, k)) gcount[(size_t)level_of(i, j, k) * 16 + group_of(i, j, k)]++;
+    plan.level_start.assign((size_t)nlevels + 1, 0);
+    std::vector<int> gstart((size_t)nlevels * 16, 0);
+    int maxc = 0;
+    for (int m = 0; m < nlevels; m++) {
+        int c = 0;
+        for (int g = 0; g < 16; g++) {
+            gstart[(size_t)m * 16 + g] = c;
+            c += gcount[(size_t)m * 16 + g];
+        }
+        plan.level_start[m + 1] = plan.level_start[m] + c;
+        maxc = std::max(maxc, c);
+    }
+    // class boundaries: groups 0-1 have zmask 0; 0-3 have no zero on y, z; 0-7 have no zero on z
+    plan.level_mid.assign((size_t)3 * nlevels, 0);
+    for (int m = 0; m < nlevels; m++) {
+        plan.level_mid[(size_t)0 * nlevels + m] = plan.level_start[m] + gstart[(size_t)m * 16 + 2];   // OPT = 8
+        plan.level_mid[(size_t)1 * nlevels + m] = plan.level_start[m] + gstart[(size_t)m * 16 + 4];   // OPT = 4
+        plan.level_mid[(size_t)2 * nlevels + m] = plan.level_start[m] + gstart[(size_t)m * 16 + 8];   // OPT = 2
+    }
+    if (maxc > 65535) {
+        err = "octant plan: level too large for 16-bit slots";
+        return false;
+    }
+    std::vector<int32_t> slot((size_t)side * side * side, -1);
+    auto sidx = [&](int i, int j, int k) { return ((size_t)i * side + j) * side + k; };
+    {
+        std::vector<int> fill((size_t)nlevels * 16, 0);
+        for (int i = 0; i <= hi; i++)
+            for (int j = 0; j <= hi; j++)
+                for (int k = 0; k <= hi; k++)
+                    if (member(i, j, k)) {
+                        const size_t g = (size_t)level_of(i, j, k) * 16 + group_of(i, j, k);
+                        slot[sidx(i, j, k)] = gstart[g] + fill[g]++;
+                    }
+    }
+    plan.cells.assign((size_t)plan.level_start[nlevels], PlanCell());
+    for (int i = 0; i <= hi; i++)
+        for (int j = 0; j <= hi; j++)
+            for (int k = 0; k <= hi; k++) {
+                if (!member(i, j, k)) continue;
+                const int m = level_of(i, j, k);
+                PlanCell pc;
+                pc.d[0] = (uint8_t)i;
+                pc.d[1] = (uint8_t)j;
+                pc.d[2] = (uint8_t)k;
+                pc.ab = 0;
+                pc.flags = (uint8_t)(zmask_of(i, j, k) << 5);
+                pc.nb[0] = pc.nb[1] = pc.nb[2] = pc.nb[3] = 0;
+                if (m == 0) {  // source cell (raytracing.cu:285-294), see build_sweep_plan
+                    pc.flags |= PC_SOURCE | PC_RATED;
+                    pc.wA = pc.wB = 0.0;
+                    pc.path = 0.5;
+                    pc.inv_np = ASORA_FOURPI;
+                } else {
+                    // one step towards the source; a zero offset steps to -1, outside the octant, with weight 0
+                    const int im = i - 1, jm = j - 1, km = k - 1;
+                    int a, b, c;
+                    int n1[3], n2[3], n3[3], n4[3];
+                    if (k >= j && k >= i) {  // raytracing.cu:394
+                        a = i; b = j; c = k;
+                        n1[0] = im; n1[1] = jm; n1[2] = km;
+                        n2[0] = i;  n2[1] = jm; n2[2] = km;
+                        n3[0] = im; n3[1] = j;  n3[2] = km;
+                        n4[0] = i;  n4[1] = j;  n4[2] = km;
+                    } else if (j >= i && j >= k) {  // raytracing.cu:446
+                        a = i; b = k; c = j;
+                        n1[0] = im; n1[1] = jm; n1[2] = km;
+                        n2[0] = i;  n2[1] = jm; n2[2] = km;
+                        n3[0] = im; n3[1] = jm; n3[2] = k;
+                        n4[0] = i;  n4[1] = jm; n4[2] = k;
+                    } else {  // raytracing.cu:491
+                        a = j; b = k; c = i;
+                        n1[0] = im; n1[1] = jm; n1[2] = km;
+                        n2[0] = im; n2[1] = j;  n2[2] = km;
+                        n3[0] = im; n3[1] = jm; n3[2] = k;
+                        n4[0] = im; n4[1] = j;  n4[2] = k;
+                    }
+                    pc.ab = (uint32_t)a | ((uint32_t)b << 8);
+                    pc.wA = (double)a / (double)c;
+                    pc.wB = (double)b / (double)c;
+                    const double da = a, db = b, dc = c;
+                    pc.path = std::sqrt((da * da + db * db) / (dc * dc) + 1.0);  // raytracing.cu:444
+                    const int n = i * i + j * j + k * k;
+                    pc.inv_np = 1.0 / ((double)n * pc.path);
+                    if (c == 1 && (a == 1 || b == 1)) pc.flags |= (a == 1 && b == 1) ? PC_DIAG3 : PC_DIAG2;
+                    if (rated(i, j, k)) pc.flags |= PC_RATED;
+                    if (k == m && j < m && i < m) pc.flags |= PC_ZFACE;
+                    const double s[4] = {pc.wA * pc.wB, pc.wB * (1.0 - pc.wA), pc.wA * (1.0 - pc.wB),
+                                         (1.0 - pc.wA) * (1.0 - pc.wB)};
+                    int* nn[4] = {n1, n2, n3, n4};
+                    for (int t = 0; t < 4; t++) {
+                        int sl = 0;
+                        if (s[t] != 0.0) {
+                            const int* q = nn[t];
+                            const bool in = q[0] >= 0 && q[1] >= 0 && q[2] >= 0 && q[0] <= hi && q[1] <= hi && q[2] <= hi;
+                            const int32_t v = in ? slot[sidx(q[0], q[1], q[2])] : -1;
+                            if (v < 0 || level_of(q[0], q[1], q[2]) != m - 1) {
+                                err = "octant plan: internal error, upstream cell not in the previous level";
+                                return false;
+                            }
+                            sl = v;
+                        }
+                        pc.nb[t] = (uint16_t)sl;
+                    }
+                }
+                plan.cells[(size_t)plan.level_start[m] + slot[sidx(i, j, k)]] = pc;
+            }
+    plan.N = N;
+    plan.R = R;
+    plan.dr = dr;
+    plan.q_max = Q;
+    plan.nlevels = nlevels;
+    plan.max_level_cells = maxc;
+    plan.lo = -hi;
+    plan.side = 2 * hi + 1;
+    plan.sphere_only = sphere_only;
+    plan.parts = 1;
+    plan.octant = true;
+    plan.ncells = (int64_t)plan.cells.size();
+    return upload ? upload_plan(plan, err) : true;
 }
 
 void free_sweep_plan(SweepPlan& plan)
@@ -294,5 +488,6 @@ void free_sweep_plan(SweepPlan& plan)
     plan.d_level_start = nullptr;
     plan.cells.clear();
     plan.level_start.clear();
+    plan.level_mid.clear();
     plan.valid = false;
 }
