@@ -192,8 +192,11 @@ int asora_set_sphere_only(int sphere_only);
 int asora_set_tuning(int sources_per_cta, int block_threads);
 
 /* Override the launch shape of the mirror-image sweep (variant 3): octants per CTA (8, 4, 2), mirror images per thread,
- * images evaluated side by side, threads per CTA; 0 = automatic for that field.  Only instantiated combinations are
- * accepted at launch time (csrc/sweep_octant.cu).  For tuning and profiling. */
+ * images evaluated side by side, threads per CTA (low 16 bits of block_threads); 0 = automatic for that field.  Only
+ * instantiated combinations are accepted at launch time (csrc/sweep_octant.cu).  Bits 16-23 of block_threads are
+ * profiling knobs: 1 = eight copies of the log2 table, 2 = toggle the (k,i,j)-ordered z-face grid copies against their
+ * automatic choice, 8 = no de-duplication of plane cells; probe builds add 4 and 16 (see launch_opts).  For tuning
+ * and profiling. */
 int asora_set_octant_shape(int octants_per_cta, int images_per_thread, int batch, int block_threads);
 
 /* Number of sweep plans built since the library was loaded (the plans are cached per mesh, radius, cell size and

@@ -10,10 +10,17 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_PKG, "csrc")
 LIB = os.path.join(_PKG, "lib", "libasora_b200.so")
 OBJ_DIR = os.path.join(_PKG, "lib", "build")
+OCT_DEFS = ["-DASORA_OCT_PROBE"] if os.environ.get("ASORA_OCT_PROBE", "1") == "1" else []
 # (source, extra defines, object name); sweep_octant.cu is compiled once per group of launch shapes
 UNITS = [("asora_api.cu", [], "asora_api.o"), ("sweep_plan.cu", [], "sweep_plan.o"), ("sweep_kernels.cu", [], "sweep_kernels.o"),
-         ("sweep_octant.cu", ["-DASORA_OCT_TU=0"], "sweep_octant_0.o"), ("sweep_octant.cu", ["-DASORA_OCT_TU=1"], "sweep_octant_1.o"),
-         ("sweep_octant.cu", ["-DASORA_OCT_TU=2"], "sweep_octant_2.o"), ("sweep_octant.cu", ["-DASORA_OCT_TU=3"], "sweep_octant_3.o"),
+         ("sweep_octant.cu", ["-DASORA_OCT_TU=0"] + OCT_DEFS, "sweep_octant_0.o"),
+         ("sweep_octant.cu", ["-DASORA_OCT_TU=1"] + OCT_DEFS, "sweep_octant_1.o"),
+         ("sweep_octant.cu", ["-DASORA_OCT_TU=2"] + OCT_DEFS, "sweep_octant_2.o"),
+         ("sweep_octant.cu", ["-DASORA_OCT_TU=3"] + OCT_DEFS, "sweep_octant_3.o"),
+         ("sweep_octant.cu", ["-DASORA_OCT_TU=4"] + OCT_DEFS, "sweep_octant_4.o"),
+         ("sweep_octant.cu", ["-DASORA_OCT_TU=5"] + OCT_DEFS, "sweep_octant_5.o"),
+         ("sweep_octant.cu", ["-DASORA_OCT_TU=6"] + OCT_DEFS, "sweep_octant_6.o"),
+         ("sweep_octant.cu", ["-DASORA_OCT_TU=7"] + OCT_DEFS, "sweep_octant_7.o"),
          ("sweep_cluster.cu", [], "sweep_cluster.o"), ("chemistry.cu", [], "chemistry.o"), ("deterministic.cu", [], "deterministic.o")]
 SOURCES = sorted({u[0] for u in UNITS})
 HEADERS = ["asora_common.cuh", "sweep_device.cuh", os.path.join("..", "..", "include", "asora_b200.h")]

@@ -82,6 +82,7 @@ struct Context {
     int tune_S = 0, tune_block = 0, tune_opts = 0;
     int tune_parts = 0;
     int oct_noct = 0, oct_opt = 0, oct_batch = 0, oct_block = 0;  // forced shape of the mirror-image sweep (0 = automatic)
+    int oct_opts = 0;                                              // its profiling knobs
     int slab_begin = 0, slab_count = 0;  // active planes of a slab-decomposed run (0 = whole grid)
     int sphere_only = 0;
     // parameters of the last sweep, for the lazily evaluated update count; and a one-entry cache of it
@@ -392,7 +393,7 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
             if (g.oct_batch > 0) batch = g.oct_batch;
             if (g.oct_block > 0) block = g.oct_block;
             if (!sweep_octant_shape_ok(noct, opt, batch, block)) return fail("mirror-image sweep: launch shape not instantiated");
-            opts = g.tune_opts & 9;  // profiling knobs: bit 0 log2-table copies, bit 3 no de-duplication of plane cells
+            opts = g.oct_opts;  // profiling knobs (asora_set_octant_shape): csrc/sweep_octant.cu, launch_opts
             variant = 3;
         }
     }
@@ -495,7 +496,7 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     bool use_z = z_possible && plan->nlevels >= 24 &&
                  (double)count * (double)(plan->ncells / plan->parts) * (variant == 3 ? 8.0 : 1.0) >= 5e8;
     if (g.tune_opts & 8 && variant == 1) use_z = !use_z && z_possible;  // profiling knob
-    if (g.tune_opts & 2 && variant == 3) use_z = !use_z && z_possible;  // profiling knob (mirror-image sweep)
+    if (g.oct_opts & 2 && variant == 3) use_z = !use_z && z_possible;  // profiling knob (mirror-image sweep)
     p.zface_offset = use_z ? (unsigned)g.ncell : 0u;
 
     // timed region (asora_last_sweep_stats: kernel_ms): nHI pre-pass, rate-grid zeroing, sweep
@@ -1104,7 +1105,8 @@ int asora_set_octant_shape(int octants_per_cta, int images_per_thread, int batch
     g.oct_noct = octants_per_cta;
     g.oct_opt = images_per_thread;
     g.oct_batch = batch;
-    g.oct_block = block_threads;
+    g.oct_opts = (block_threads >> 16) & 0xff;
+    g.oct_block = block_threads & 0xffff;
     return 0;
 }
 

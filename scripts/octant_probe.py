@@ -14,6 +14,8 @@ from tests.test_gpu_octant import SHAPES, BIG
 N = 256
 ns = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 radii = [float(x) for x in sys.argv[2:]] or [30.0, 10.76]
+ONLY = [tuple(int(v) for v in t.split(",")) for t in os.environ.get("ASORA_PROBE_SHAPES", "").split(";") if t]
+KNOBS = [int(x) for x in os.environ.get("ASORA_PROBE_KNOBS", "0,1,4,5,8,16,2").split(",")]
 thin, thick, dlogtau = p.blackbody_tables(1e5, False, -20.0, 4.0, 20000)
 p.device_init(N, 64); p.photo_table_to_device(thin, thick)
 nd, xh = f0_fields(N)
@@ -48,15 +50,16 @@ for R in radii:
               f"{n*cells/kms/1e6:.1f} G updates/s (full cell count)", flush=True)
         check(L.asora_set_sweep_variant(3))
         for shape in SHAPES:
-            if shape[0] != 8:
+            if ONLY and shape not in ONLY:
                 continue
             if R > 20 and shape not in BIG:
                 continue
-            if R < 20 and shape[3] > 512:
+            if R < 20 and (shape[3] > 512 or shape[0] != 8):
                 continue
-            check(L.asora_set_octant_shape(*shape))
-            for knobs in ((0, 2, 3, 8) if (R > 20 and sphere == 0) else (0,)):
-                check(L.asora_set_tuning(0, knobs << 16))
+            # knobs: 1 log2 copies, 2 toggle the z-face copies (automatic: on for large sweeps), 4 plan entry prefetched,
+            # 8 no de-duplication, 16 table gathers by LDG
+            for knobs in (KNOBS if (R > 20 and sphere == 0) else ((0, 4) if shape not in BIG else (0,))):
+                check(L.asora_set_octant_shape(*shape[:3], shape[3] | (knobs << 16)))
                 try:
                     ms, kms = run(R, n)
                 except RuntimeError as e:

@@ -8,11 +8,28 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-# (octants per CTA, images per thread, batch, threads) -- ASORA_OCT_SHAPES_* in csrc/sweep_octant.cu
-SHAPES = [(8, 8, 8, 256), (8, 8, 4, 256), (8, 8, 4, 384), (8, 8, 2, 512), (8, 4, 4, 384), (8, 4, 2, 512), (8, 4, 2, 768),
-          (8, 2, 2, 768), (8, 8, 2, 128), (8, 8, 2, 64), (8, 4, 2, 256), (8, 4, 2, 128), (4, 4, 4, 256), (4, 4, 2, 512),
-          (2, 2, 2, 512), (2, 2, 2, 256)]
-BIG = [s for s in SHAPES if s not in ((8, 8, 2, 128), (8, 8, 2, 64), (8, 4, 2, 256), (8, 4, 2, 128))]
+import os
+import re
+
+
+def _instantiated_shapes():
+    """(octants per CTA, images per thread, batch, threads, big) of every instantiated launch shape, read from the
+    ASORA_OCT_SHAPES_* tables of csrc/sweep_octant.cu."""
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pyc2ray_b200", "csrc",
+                            "sweep_octant.cu")).read()
+    out = []
+    for line in src.splitlines():
+        if line.startswith("#define ASORA_OCT_SHAPES_"):
+            for m in re.finditer(r"X\((\d+), (\d+), (\d+), (\d+), (\d+), (true|false)\)", line):
+                no, op, ba, bl, mb, big = m.groups()
+                out.append((int(no), int(op), int(ba), int(bl), big == "true"))
+    return out
+
+
+ALL = _instantiated_shapes()
+assert len(ALL) >= 16, "could not read the shape tables of csrc/sweep_octant.cu"
+SHAPES = [s[:4] for s in ALL]
+BIG = [s[:4] for s in ALL if s[4]]
 
 
 def _oracle(c):
@@ -31,11 +48,10 @@ def test_octant_shapes_vs_oracle(name, shape):
     ref, _, n = _oracle(c)
     _setup(libasora, c)
     try:
-        _cabi.check(_cabi.L.asora_set_octant_shape(*shape))
         for sphere_only in (0, 1):
             _cabi.check(_cabi.L.asora_set_sphere_only(sphere_only))
-            for knobs in (0, 8):  # bit 3: every entry as class A (no de-duplication of plane cells)
-                _cabi.check(_cabi.L.asora_set_tuning(0, knobs << 16))
+            for knobs in (0, 8, 4):  # bit 3: every entry as class A (no de-duplication of plane cells), bit 2: plan entry prefetched
+                _cabi.check(_cabi.L.asora_set_octant_shape(*shape[:3], shape[3] | (knobs << 16)))
                 phi, used, upd = _sweep(libasora, _cabi, c, 3)
                 assert used == 3
                 if not sphere_only:
@@ -77,22 +93,20 @@ def test_octant_bench_radius_vs_oracle_and_variant1():
         for shape in BIG:
             if shape[0] != 8:
                 continue  # all eight octants of R = 30 fit in one CTA; the split shapes are exercised below
-            _cabi.check(_cabi.L.asora_set_octant_shape(*shape))
-            for knobs in (0, 2, 3, 8, 10):  # bit 1: z-face copies on, bit 0: log2 copies, bit 3: no de-duplication
-                _cabi.check(_cabi.L.asora_set_tuning(0, knobs << 16))
+            for knobs in (0, 2, 3, 8, 10, 6, 7, 5, 13):  # bit 1: z-face copies on, bit 0: log2 copies, bit 3: no de-duplication,
+                                                     # bit 2: plan entry prefetched
+                _cabi.check(_cabi.L.asora_set_octant_shape(*shape[:3], shape[3] | (knobs << 16)))
                 phi, used, upd = _sweep(libasora, _cabi, c, 3)
                 assert used == 3 and upd == n
                 _assert_close(phi, ref, f"R=30 shape={shape} knobs={knobs}")
                 _assert_close(phi, v1, f"R=30 shape={shape} knobs={knobs} vs variant 1", rtol=1e-11)
         for shape in [s for s in BIG if s[0] != 8]:
-            _cabi.check(_cabi.L.asora_set_octant_shape(*shape))
             for knobs in (0, 2):
-                _cabi.check(_cabi.L.asora_set_tuning(0, knobs << 16))
+                _cabi.check(_cabi.L.asora_set_octant_shape(*shape[:3], shape[3] | (knobs << 16)))
                 phi, used, upd = _sweep(libasora, _cabi, c, 3)
                 _assert_close(phi, ref, f"R=30 split shape={shape} knobs={knobs}")
         # automatic shape, sphere-only, z-face copies, two accumulating sweeps
-        _cabi.check(_cabi.L.asora_set_octant_shape(0, 0, 0, 0))
-        _cabi.check(_cabi.L.asora_set_tuning(0, 2 << 16))
+        _cabi.check(_cabi.L.asora_set_octant_shape(0, 0, 0, 2 << 16))
         _cabi.check(_cabi.L.asora_set_sphere_only(1))
         phi, used, _ = _sweep(libasora, _cabi, c, 3)
         _cabi.check(_cabi.L.asora_set_sphere_only(0))
