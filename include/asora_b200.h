@@ -62,6 +62,15 @@ int asora_source_data_to_device(const int32_t* pos, const double* flux, int NumS
 int asora_do_all_sources(double R, double sig, double dr, const double* xh_av, double* phi_ion,
                          int NumSrc, int N, double minlogtau, double dlogtau, int NumTau);
 
+/* The two halves of asora_do_all_sources, for callers that put a collective between the sweep and the download (one
+ * process per GPU, sources sharded over the ranks, pyc2ray/evolve.py:360-373,433-437): _begin copies xh_av to the
+ * device and queues the sweep of the first NumSrc uploaded sources on the context's stream; the caller then reduces
+ * ASORA_BUF_PHI_ION over the ranks on that stream (asora_set_stream, asora_device_buffer); _end waits and copies the
+ * rates to phi_ion, or only waits when phi_ion is NULL (a rank that does not need the grid on the host). */
+int asora_do_all_sources_begin(double R, double sig, double dr, const double* xh_av, int NumSrc, int N,
+                               double minlogtau, double dlogtau, int NumTau);
+int asora_do_all_sources_end(double* phi_ion);
+
 /* ---- photo-heating rates --------------------------------------------------------------
  * The reference computes phi_heat only in its CPU ray tracer (src/c2ray/photorates.f90:118,124,
  * src/c2ray/raytracing.f90:530,537; f2py arguments heat_thin_table, heat_thick_table, phi_heat of
@@ -73,7 +82,11 @@ int asora_do_all_sources(double R, double sig, double dr, const double* xh_av, d
 int asora_heat_table_to_device(const double* heat_thin_table, const double* heat_thick_table, int NumTau);
 
 /* Heating on/off for the device-resident sweeps (asora_raytrace_device): when on, ASORA_BUF_PHI_HEAT receives
- * the sum over sources of heat / nHI next to ASORA_BUF_PHI_ION. */
+ * the sum over sources of heat / nHI next to ASORA_BUF_PHI_ION.  Restrictions while heating is on: sweeps must zero
+ * the rate grids (zero_phi != 0; accumulating on top of earlier rates is an error) and the single-source debug path
+ * (asora_debug_single_source) is not available.  The thin-cell branch evaluates the heating table at tau_out, the
+ * convention of the ASORA ionisation rate (rates.cu:37); the CPU ray tracer uses tau_in (photorates.f90:124), a
+ * relative difference below 1e-7 (|tau_out - tau_in| <= 1e-7 in that branch). */
 int asora_set_heating(int on);
 
 /* asora_do_all_sources that also returns the photo-heating rates (host, N^3). */
@@ -108,8 +121,12 @@ enum {
     ASORA_BUF_COUNT = 8
 };
 
-/* Device address of a named buffer (allocated on first use), or NULL on error. */
+/* Device address of a named buffer (allocated on first use), or NULL on error.  The chemistry caches two
+ * temperature-only factors per cell (chemistry.f90:257-262) for the contents of ASORA_BUF_TEMP; every library call that
+ * can change that buffer (upload, copy, this function) drops the cache.  A caller that keeps the pointer returned for
+ * ASORA_BUF_TEMP and writes through it later must call asora_invalidate_temperature() before the next chemistry pass. */
 void* asora_device_buffer(int which);
+int asora_invalidate_temperature(void);
 
 /* Host -> device / device -> host copy of a named buffer (N^3 doubles). */
 int asora_buffer_upload(int which, const double* host);

@@ -6,6 +6,8 @@
 #include "../../include/asora_b200.h"
 #include "asora_common.cuh"
 
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges show up under nsys / ncu --nvtx, no-ops otherwise
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -78,7 +80,6 @@ struct Context {
     int64_t chem_stage_n = 0;
     // stats of the last sweep
     int variant_forced = 0;
-    bool auto_octant = false;  // automatic selection may pick the mirror-image sweep
     int tune_S = 0, tune_block = 0, tune_opts = 0;
     int tune_parts = 0;
     int oct_noct = 0, oct_opt = 0, oct_batch = 0, oct_block = 0;  // forced shape of the mirror-image sweep (0 = automatic)
@@ -127,6 +128,12 @@ void free_tables()
     g.heating = false;
 }
 
+// NVTX range for the lifetime of the object (tracing)
+struct Range {
+    explicit Range(const char* name) { nvtxRangePushA(name); }
+    ~Range() { nvtxRangePop(); }
+};
+
 int need_init()
 {
     if (!g.init) return fail("GPU not initialized. Please initialize it by calling device_init(N)");
@@ -142,6 +149,9 @@ int ensure_buffer(int which)
         const size_t n = (size_t)g.ncell * (twice ? 2 : 1);
         CK(cudaMalloc(&g.buf[which], sizeof(double) * n));
         CK(cudaMemsetAsync(g.buf[which], 0, sizeof(double) * n, g.stream));
+        // a temperature grid means chemistry passes will follow: their factor grid is allocated with it, so that the
+        // first pass of a time step does not pay a 16 N^3-byte cudaMalloc
+        if (which == ASORA_BUF_TEMP && !g.chem_factors) CK(cudaMalloc(&g.chem_factors, sizeof(double2) * g.ncell));
     }
     return 0;
 }
@@ -152,6 +162,7 @@ int ensure_buffer(int which)
 // bounce buffers and streams, double-buffered, which is limited by PCIe instead.  Synchronous, like the API.
 int host_copy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind)
 {
+    Range range(kind == cudaMemcpyHostToDevice ? "asora:h2d" : "asora:d2h");
     const void* host = (kind == cudaMemcpyHostToDevice) ? src : dst;
     cudaPointerAttributes attr;
     bool pinned = false;
@@ -364,7 +375,11 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     const int hi_cells = std::min(p.q_max, std::max(-p.last_l, p.last_r));
     const bool symmetric = std::min(p.q_max, p.last_r) == std::min(p.q_max, -p.last_l) && hi_cells <= 126;
     const size_t budget = (size_t)g.smem_optin;
-    if ((variant == 3 || (variant == 0 && g.auto_octant)) && symmetric && !coldens_grid) {
+    // automatic choice (measured, scripts/octant_probe.py): the mirror-image sweep wins on full-octahedron sweeps of large
+    // radii (R = 30: 16.3 vs 17.0 ms); sphere-only sweeps and small radii stay on variant 1 (R = 30 sphere-only: 11.2 vs
+    // 11.9 ms; R = 10.76: 8.4 vs 11.3 ms)
+    const bool auto_octant = !sphere_only && hi_cells >= 32 && !g.heating;
+    if ((variant == 3 || (variant == 0 && auto_octant)) && symmetric && !coldens_grid) {
         std::string err;
         plan = get_plan(N, R, dr, sphere_only, true, 1, err);
         if (!plan && variant == 3) return fail(err);
@@ -378,22 +393,30 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
             }
         }
         if (plan) {
-            // Launch shape (measured on B200, scripts/octant_probe.py): see DESIGN.md, "Mirror-image sweep"
+            // Launch shape (measured on B200, scripts/octant_probe.py; DESIGN.md, "Mirror-image sweep").  Large levels:
+            // half-spaces as separate CTAs, two of them per SM, four images per thread evaluated side by side, the next
+            // plan entry prefetched, plane cells recomputed (the de-duplicated path costs more than the 3 % of cells it
+            // saves at R = 30: 16.3 vs 16.4-17.9 ms); small levels: de-duplication on (24 % of the cells at R = 10).
             const int maxc = plan->max_level_cells;
+            int auto_opts = 0;
+            if (g.oct_noct == 0 && maxc >= 512 && sweep_octant_smem_bytes(*plan, 4, 1, true) * 2 + 2048 <= (size_t)g.smem_per_sm) noct = 4;
             if (noct == 8) {
-                if (maxc >= 512) { opt = 8; batch = 4; block = 384; }
-                else if (maxc >= 128) { opt = 4; batch = 2; block = 256; }
-                else { opt = 8; batch = 2; block = 64; }
+                if (maxc >= 512) { opt = 4; batch = 2; block = 512; }
+                else if (maxc >= 128) { opt = 4; batch = 2; block = 128; }
+                else { opt = 2; batch = 1; block = 128; }
             } else if (noct == 4) {
                 opt = 4; batch = 4; block = 256;
+                auto_opts = 4 | 8;
             } else {
-                opt = 2; batch = 2; block = 256;
+                opt = 2; batch = 2; block = 192;
+                auto_opts = 8;
             }
             if (g.oct_opt > 0) opt = g.oct_opt;
             if (g.oct_batch > 0) batch = g.oct_batch;
             if (g.oct_block > 0) block = g.oct_block;
             if (!sweep_octant_shape_ok(noct, opt, batch, block)) return fail("mirror-image sweep: launch shape not instantiated");
-            opts = g.oct_opts;  // profiling knobs (asora_set_octant_shape): csrc/sweep_octant.cu, launch_opts
+            // profiling knobs (asora_set_octant_shape; csrc/sweep_octant.cu: launch_opts) replace the automatic options
+            opts = (g.oct_opts || g.oct_noct || g.oct_opt || g.oct_batch || g.oct_block) ? g.oct_opts : auto_opts;
             variant = 3;
         }
     }
@@ -502,6 +525,7 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     // timed region (asora_last_sweep_stats: kernel_ms): nHI pre-pass, rate-grid zeroing, sweep
     CK(cudaEventRecord(g.ev0, g.stream));
     {
+        Range prepass_range("asora:opacity_prepass");
         // whole grid, or the (periodic) range of planes this rank's sweeps can touch: at most two segments
         const int64_t plane = (int64_t)N * N;
         int64_t seg_off[2] = {0, 0}, seg_len[2] = {g.ncell, 0};
@@ -538,6 +562,8 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
         }
     }
 
+    {
+    Range sweep_range("asora:sweep");
     CK(cudaEventRecord(g.evk0, g.stream));
     if (variant == 1) {
         g.last_levels = plan->nlevels;
@@ -553,6 +579,8 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
         if (e != cudaSuccess) return fail_cuda("sweep_grid_kernel launch", e);
     }
     CK(cudaEventRecord(g.evk1, g.stream));
+    }
+    Range finish_range("asora:finish_phi");
     {   // phi = sum / ntau over the planes the sweep could touch
         const int64_t plane = (int64_t)N * N;
         int64_t seg_off[2] = {0, 0}, seg_len[2] = {g.ncell, 0};
@@ -639,6 +667,7 @@ int asora_device_init(int N, int num_src_par)
     if (int rc = ensure_buffer(ASORA_BUF_NDENS)) return rc;
     if (int rc = ensure_buffer(ASORA_BUF_XH_AV)) return rc;
     if (int rc = ensure_buffer(ASORA_BUF_PHI_ION)) return rc;
+    if (int rc = ensure_chem_scratch()) return rc;
     CK(cudaStreamSynchronize(g.stream));
     // the reference prints the device and the allocation (memory.cu:52-59,77-78); ASORA_QUIET=1 silences it
     const char* quiet = getenv("ASORA_QUIET");
@@ -875,6 +904,28 @@ int asora_do_all_sources(double R, double sig, double dr, const double* xh_av, d
     return 0;
 }
 
+int asora_do_all_sources_begin(double R, double sig, double dr, const double* xh_av, int NumSrc, int N, double minlogtau,
+                               double dlogtau, int NumTau)
+{
+    if (int rc = need_init()) return rc;
+    if (N != g.N) return fail("do_all_sources_begin: m1 differs from device_init");
+    if (!xh_av) return fail("do_all_sources_begin: null pointer");
+    if (int rc = host_copy(g.buf[ASORA_BUF_XH_AV], xh_av, sizeof(double) * g.ncell, cudaMemcpyHostToDevice)) return rc;
+    return run_sweep(R, sig, dr, 0, NumSrc, minlogtau, dlogtau, NumTau, true, nullptr);
+}
+
+int asora_do_all_sources_end(double* phi_ion)
+{
+    if (int rc = need_init()) return rc;
+    if (phi_ion) {
+        if (int rc = host_copy(phi_ion, g.buf[ASORA_BUF_PHI_ION], sizeof(double) * g.ncell, cudaMemcpyDeviceToHost)) return rc;
+    } else {
+        CK(cudaStreamSynchronize(g.stream));
+    }
+    if (g.last_launches > 0) cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1);
+    return 0;
+}
+
 int asora_debug_single_source(double R, double sig, double dr, const double* xh_av, int src_index,
                               double minlogtau, double dlogtau, int NumTau, double* coldensh_out, double* phi_ion)
 {
@@ -993,6 +1044,7 @@ int asora_global_pass_device_range(double dt, double bh00, double albpow, double
                                    int64_t cell_offset, int64_t cell_count, int* conv_flag, double* sum_xh1,
                                    double* sum_xh0)
 {
+    Range range("asora:chemistry");
     if (int rc = need_init()) return rc;
     if (cell_offset < 0 || cell_count < 0 || cell_offset + cell_count > g.ncell)
         return fail("global_pass_device_range: range outside the grid");
@@ -1032,6 +1084,7 @@ int asora_buffer_copy(int dst, int src)
 int asora_global_pass_device(double dt, double bh00, double albpow, double colh0, double temph0, double abu_c,
                              int* conv_flag, double* sum_xh1, double* sum_xh0)
 {
+    Range range("asora:chemistry");
     if (int rc = need_init()) return rc;
     const int ids[] = {ASORA_BUF_NDENS, ASORA_BUF_TEMP, ASORA_BUF_XH, ASORA_BUF_XH_AV, ASORA_BUF_XH_INTERMED,
                        ASORA_BUF_PHI_ION};
@@ -1053,6 +1106,7 @@ int asora_global_pass(double dt, const double* ndens, const double* temp, const 
                       double* xh_intermed, const double* phi_ion, double bh00, double albpow, double colh0,
                       double temph0, double abu_c, int64_t ncell, int* conv_flag)
 {
+    Range range("asora:chemistry");
     if (ncell <= 0) return fail("global_pass: ncell must be positive");
     if (!ndens || !temp || !xh || !xh_av || !xh_intermed || !phi_ion) return fail("global_pass: null pointer");
     cudaStream_t st = g.init ? g.stream : (cudaStream_t)0;
@@ -1086,6 +1140,12 @@ int asora_global_pass(double dt, const double* ndens, const double* temp, const 
     if (xh_intermed != xh_av) CK(cudaMemcpyAsync(xh_intermed, dev[4], bytes, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (conv_flag) *conv_flag = flag;
+    return 0;
+}
+
+int asora_invalidate_temperature(void)
+{
+    g.chem_factors_valid = false;
     return 0;
 }
 

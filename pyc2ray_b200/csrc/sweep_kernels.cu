@@ -357,8 +357,10 @@ __device__ __forceinline__ void group_barrier(unsigned* counter, unsigned nctas,
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(counter, 1u);
+        // the counter only ever grows; comparing the wrapped difference keeps the barrier correct after 2^32 arrivals
+        // (many sources on few groups at large meshes)
         const unsigned target = epoch * nctas;
-        while (*(volatile unsigned*)counter < target) {
+        while ((int)(*(volatile unsigned*)counter - target) < 0) {
         }
         __threadfence();
     }

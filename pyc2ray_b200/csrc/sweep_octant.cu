@@ -210,6 +210,7 @@ __device__ __forceinline__ void octant_level(const int4* __restrict__ plan, int 
                                              const SweepParams& p, const double2* __restrict__ log2_tab)
 {
     constexpr int G = NOCT / OPT;                 // warps that share an entry
+    static_assert((BLOCK / 32) % G == 0 && BLOCK % 32 == 0, "the warps of a CTA must divide evenly over the image groups");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sub = (G > 1) ? (warp % G) : 0;
     const int obase = sub * OPT;                  // local octants [obase, obase + OPT)
@@ -379,8 +380,8 @@ cudaError_t launch_opts(const SweepPlan& plan, const SweepParams& p, int opts, c
 #define ASORA_OCT_SHAPES_2(X) X(2, 2, 2, 192, 4, true) X(2, 2, 2, 128, 5, true) X(2, 2, 2, 256, 2, true)
 #define ASORA_OCT_SHAPES_3(X) X(8, 2, 1, 896, 1, true) X(8, 8, 4, 384, 1, true) X(4, 2, 1, 448, 2, true)
 #define ASORA_OCT_SHAPES_4(X) X(8, 2, 1, 128, 7, false) X(8, 4, 2, 128, 4, false) X(8, 4, 1, 128, 6, false)
-#define ASORA_OCT_SHAPES_5(X) X(8, 2, 1, 256, 3, false) X(8, 4, 2, 256, 2, false) X(8, 8, 2, 64, 8, false)
-#define ASORA_OCT_SHAPES_6(X) X(8, 2, 2, 64, 8, false) X(8, 2, 1, 64, 14, false) X(8, 2, 2, 128, 4, false)
+#define ASORA_OCT_SHAPES_5(X) X(8, 2, 1, 256, 3, false) X(8, 4, 2, 256, 2, false) X(8, 8, 2, 64, 8, false) X(8, 4, 2, 64, 8, false)
+#define ASORA_OCT_SHAPES_6(X) X(8, 2, 2, 128, 4, false) X(8, 4, 1, 64, 12, false)
 #define ASORA_OCT_SHAPES_7(X) X(2, 2, 2, 160, 4, true) X(2, 2, 2, 224, 3, true) X(4, 2, 2, 320, 2, true)
 #define ASORA_OCT_NTU 8
 #if ASORA_OCT_TU == 0

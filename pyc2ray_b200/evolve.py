@@ -107,7 +107,6 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
             chunk = NumCells // nprocs
         if halo is not None:
             xav_t = device_tensor(L.asora_device_buffer(_cabi.BUF_XH_AV), NumCells)
-            check(L.asora_set_active_slab(*halo.active_range()))
             scal = torch.zeros(3, dtype=torch.float64, device="cuda")
 
     if rank == 0 and not (quiet and logfile is None):  # (the two grid means below cost 22 ms at 250^3)
@@ -118,21 +117,26 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
         printlog(f"Mean density (cgs): {ndens.mean():.3e}, Mean ionized fraction: {xh.mean():.3e}", logfile, quiet)
         printlog(f"Convergence Criterion (Number of points): {conv_criterion : n}", logfile, quiet, end="\n\n")
 
-    # The evolve loop only consumes phi_ion, so the sweep may skip the cells outside the R_max sphere
-    # (identical rates, see asora_set_sphere_only in include/asora_b200.h).
-    check(L.asora_set_sphere_only(1))
     converged = False
     niter = 0
     flag = ctypes.c_int(0)
     s1 = ctypes.c_double(0.0)
     s0 = ctypes.c_double(0.0)
     try:
+        # process-global sweep settings: switched on inside the try so that the finally below always resets them
+        # The evolve loop only consumes phi_ion, so the sweep may skip the cells outside the R_max sphere
+        # (identical rates, see asora_set_sphere_only in include/asora_b200.h).
+        check(L.asora_set_sphere_only(1))
+        if halo is not None:
+            check(L.asora_set_active_slab(*halo.active_range()))
         while not converged:
             niter += 1
             trt0 = time.time()
             check(L.asora_raytrace_device(float(R_max_LLS), float(sig), float(dr), 0, NumSrc, float(minlogtau),
                                           float(dlogtau), int(NumTau), 1))
             check(L.asora_sync())
+            if nprocs > 1:
+                torch.cuda.nvtx.range_push("asora:exchange_phi")
             if halo is not None:
                 halo.reduce_phi_(phi_t)       # neighbours' rates for my planes: 2 halos of h*N^2 doubles
                 torch.cuda.synchronize()
@@ -142,6 +146,8 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
             elif nprocs > 1:
                 allreduce_sum_(phi_t, group)  # evolve.py:433-437 (Reduce + Bcast) as one NCCL all-reduce
                 torch.cuda.synchronize()
+            if nprocs > 1:
+                torch.cuda.nvtx.range_pop()
             trt = time.time() - trt0
             tch0 = time.time()
             if halo is not None:
@@ -185,8 +191,7 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
                 raise RuntimeError("evolve3D: no convergence")
     finally:
         L.asora_set_sphere_only(0)
-        if halo is not None:
-            L.asora_set_active_slab(0, 0)
+        L.asora_set_active_slab(0, 0)
     if rsag:
         # once per time step: every rank gets the whole grids back (the reference API returns full arrays)
         allgather_chunks_(device_tensor(L.asora_device_buffer(_cabi.BUF_XH_INTERMED), NumCells), rank, nprocs, group)

@@ -25,6 +25,9 @@ SIGNATURES = {
     "asora_photo_table_to_device": (_i, [c_dp, c_dp, _i]),
     "asora_source_data_to_device": (_i, [c_ip, c_dp, _i]),
     "asora_do_all_sources": (_i, [_d, _d, _d, c_dp, c_dp, _i, _i, _d, _d, _i]),
+    "asora_do_all_sources_begin": (_i, [_d, _d, _d, c_dp, _i, _i, _d, _d, _i]),
+    "asora_do_all_sources_end": (_i, [c_dp]),
+    "asora_invalidate_temperature": (_i, []),
     "asora_heat_table_to_device": (_i, [c_dp, c_dp, _i]),
     "asora_set_heating": (_i, [_i]),
     "asora_do_all_sources_heat": (_i, [_d, _d, _d, c_dp, c_dp, c_dp, _i, _i, _d, _d, _i]),

@@ -64,9 +64,16 @@ def source_data_to_device(pos, flux, NumSrc):
     check(L.asora_source_data_to_device(iptr(pos), dptr(flux), int(NumSrc)))
 
 
-def do_all_sources(R, coldensh_out, sig, dr, ndens, xh_av, phi_ion, NumSrc, m1, minlogtau, dlogtau, NumTau):
+def do_all_sources(R, coldensh_out, sig, dr, ndens, xh_av, phi_ion, NumSrc, m1, minlogtau, dlogtau, NumTau, group=None,
+                   download=True):
     """python_module.cu:21-68.  ``coldensh_out`` and ``ndens`` are accepted and ignored exactly as the
-    reference ignores them (raytracing.cu:116); ``phi_ion`` is overwritten in place."""
+    reference ignores them (raytracing.cu:116); ``phi_ion`` is overwritten in place.
+
+    ``group`` (keyword, not in the reference): a torch.distributed process group (or True for the default group) whose
+    ranks each hold a shard of the sources on their own GPU.  The rates of all ranks are then summed on the devices by
+    one NCCL all-reduce between the sweep and the download -- the reference's Reduce + Bcast of host arrays
+    (pyc2ray/evolve.py:433-437) -- and ``download=False`` lets a rank skip the device-to-host copy when it does not
+    need the grid on the host."""
     if not isinstance(coldensh_out, np.ndarray) or coldensh_out.dtype != np.float64:
         raise TypeError("coldensh_out must be Array of type double")  # python_module.cu:53-57
     n3 = int(m1) ** 3
@@ -74,8 +81,21 @@ def do_all_sources(R, coldensh_out, sig, dr, ndens, xh_av, phi_ion, NumSrc, m1, 
     _f64(phi_ion, "phi_ion", n3)
     if not phi_ion.flags.writeable:
         raise ValueError("phi_ion must be writeable")
-    check(L.asora_do_all_sources(float(R), float(sig), float(dr), dptr(xh_av), dptr(phi_ion), int(NumSrc),
-                                 int(m1), float(minlogtau), float(dlogtau), int(NumTau)))
+    if group is None:
+        check(L.asora_do_all_sources(float(R), float(sig), float(dr), dptr(xh_av), dptr(phi_ion), int(NumSrc),
+                                     int(m1), float(minlogtau), float(dlogtau), int(NumTau)))
+        return
+    import torch
+    import torch.distributed as dist
+    from ..parallel import device_tensor
+    check(L.asora_do_all_sources_begin(float(R), float(sig), float(dr), dptr(xh_av), int(NumSrc), int(m1), float(minlogtau),
+                                       float(dlogtau), int(NumTau)))
+    phi_t = device_tensor(L.asora_device_buffer(_cabi.BUF_PHI_ION), n3)
+    torch.cuda.nvtx.range_push("asora:allreduce_phi")
+    dist.all_reduce(phi_t, op=dist.ReduceOp.SUM, group=None if group is True else group)
+    torch.cuda.synchronize()
+    torch.cuda.nvtx.range_pop()
+    check(L.asora_do_all_sources_end(dptr(phi_ion) if download else None))
 
 
 # ---- photo-heating rates: not in the reference's libasora (TODO at c2ray_base.py:424-426); the signatures extend

@@ -1,5 +1,6 @@
-"""Throughput against ray-tracing radius and source count (the axes of the reference's raytracing_benchmark), 256^3,
-device-resident inputs, automatic launch shape.  Prints a markdown table."""
+"""Throughput against ray-tracing radius and source count (the axes of the reference's raytracing_benchmark:
+test/paper_tests/raytracing_benchmark/run_test.py:24,48,82-93), mesh 256 (BASELINE) or 250 (the paper's own; ASORA_SWEEP_MESH),
+device-resident inputs, automatic launch shape.  Prints a markdown table.  Also reachable as `python bench.py --sweep`."""
 import ctypes, sys, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,7 +10,7 @@ from pyc2ray_b200.lib import _cabi, libasora
 from pyc2ray_b200.lib._cabi import L, check
 from tests.fields import f0_fields, MPC, SIG
 thin, thick, dlogtau = p.blackbody_tables(1e5, False, -20.0, 4.0, 20000)
-N = 256
+N = int(os.environ.get("ASORA_SWEEP_MESH", "256"))
 p.device_init(N, 64); p.photo_table_to_device(thin, thick)
 nd, xh = f0_fields(N)
 libasora.density_to_device(np.ascontiguousarray(nd.ravel()), N)
