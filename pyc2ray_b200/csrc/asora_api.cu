@@ -86,6 +86,11 @@ struct Context {
     int oct_opts = 0;                                              // its profiling knobs
     int slab_begin = 0, slab_count = 0;  // active planes of a slab-decomposed run (0 = whole grid)
     int sphere_only = 0;
+    int deterministic = 0;            // asora_set_deterministic: fixed-point accumulation of the rates
+    long long* det_lo = nullptr;      // low parts of the fixed-point sums (N^3), and of the heating sums
+    long long* det_lo_heat = nullptr;
+    double flux_max = 0.0;            // largest uploaded source flux
+    double table_max = 0.0;           // largest |table entry| (photo and heating tables): bounds one cell's absorbed fraction
     // parameters of the last sweep, for the lazily evaluated update count; and a one-entry cache of it
     int last_count = 0;
     double last_R = 0, last_dr = 0;
@@ -342,6 +347,22 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
         if (int rc = ensure_buffer(ASORA_BUF_PHI_HEAT)) return rc;
         p.phi_heat = g.buf[ASORA_BUF_PHI_HEAT];
     }
+    p.det_lo = p.det_lo_heat = nullptr;
+    p.det_scale = 0.0;
+    if (g.deterministic) {
+        if (coldens_grid) return fail("deterministic accumulation is not available on the single-source debug path");
+        // largest possible contribution: strength * kpref * 4 pi (source cell) * (difference of two table entries)
+        const double vmax = 2.0 * g.flux_max * p.kpref * ASORA_FOURPI * g.table_max;
+        int e2 = 0;
+        std::frexp(vmax > 0.0 ? vmax : 1.0, &e2);  // vmax < 2^e2
+        p.det_scale = std::ldexp(1.0, 82 - e2);   // contributions stay below 2^82 = 2^42 high parts of 2^40
+        if (!g.det_lo) CK(cudaMalloc(&g.det_lo, sizeof(long long) * g.ncell));
+        p.det_lo = g.det_lo;
+        if (p.phi_heat) {
+            if (!g.det_lo_heat) CK(cudaMalloc(&g.det_lo_heat, sizeof(long long) * g.ncell));
+            p.det_lo_heat = g.det_lo_heat;
+        }
+    }
     p.thin = g.thin;
     p.thick = g.thick;
     p.tex_pairs = g.tex_pairs;
@@ -515,7 +536,7 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     const bool slab_active = g.slab_count > 0 && g.slab_count < N;
     const bool z_shape = (variant == 1 && S == 1 && block >= 768) || (variant == 3 && noct * plan->max_level_cells >= 2048 && !p.phi_heat &&
                                                                          sweep_octant_shape_ok(noct, opt, batch, block) == 2);
-    const bool z_possible = z_shape && g.zface_ok && !coldens_grid && !slab_active;
+    const bool z_possible = z_shape && g.zface_ok && !coldens_grid && !slab_active && !g.deterministic;
     bool use_z = z_possible && plan->nlevels >= 24 &&
                  (double)count * (double)(plan->ncells / plan->parts) * (variant == 3 ? 8.0 : 1.0) >= 5e8;
     if (g.tune_opts & 8 && variant == 1) use_z = !use_z && z_possible;  // profiling knob
@@ -559,6 +580,8 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
             }
             CK(cudaMemsetAsync(g.buf[ASORA_BUF_PHI_ION] + seg_off[sg], 0, sizeof(double) * seg_len[sg], g.stream));
             if (p.phi_heat) CK(cudaMemsetAsync(p.phi_heat + seg_off[sg], 0, sizeof(double) * seg_len[sg], g.stream));
+            if (p.det_lo) CK(cudaMemsetAsync(p.det_lo + seg_off[sg], 0, sizeof(long long) * seg_len[sg], g.stream));
+            if (p.det_lo_heat) CK(cudaMemsetAsync(p.det_lo_heat + seg_off[sg], 0, sizeof(long long) * seg_len[sg], g.stream));
         }
     }
 
@@ -603,11 +626,22 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
         }
         for (int sg = 0; sg < 2 && !use_z; sg++) {
             if (seg_len[sg] <= 0) continue;
-            cudaError_t e = launch_finish_phi(g.buf[ASORA_BUF_PHI_ION] + seg_off[sg], g.nhi + seg_off[sg],
-                                              zero_phi ? nullptr : g.phi_keep + seg_off[sg], seg_len[sg], g.stream);
-            if (e == cudaSuccess && p.phi_heat) {  // raytracing.f90:530: the heating rate is divided by nHI as well
-                e = launch_finish_phi(p.phi_heat + seg_off[sg], g.nhi + seg_off[sg], nullptr, seg_len[sg], g.stream);
-                g.last_launches += 1;
+            cudaError_t e;
+            if (p.det_lo) {
+                e = launch_finish_phi_fixed(g.buf[ASORA_BUF_PHI_ION] + seg_off[sg], p.det_lo + seg_off[sg], g.nhi + seg_off[sg],
+                                            zero_phi ? nullptr : g.phi_keep + seg_off[sg], 1.0 / p.det_scale, seg_len[sg], g.stream);
+                if (e == cudaSuccess && p.phi_heat) {
+                    e = launch_finish_phi_fixed(p.phi_heat + seg_off[sg], p.det_lo_heat + seg_off[sg], g.nhi + seg_off[sg], nullptr,
+                                                1.0 / p.det_scale, seg_len[sg], g.stream);
+                    g.last_launches += 1;
+                }
+            } else {
+                e = launch_finish_phi(g.buf[ASORA_BUF_PHI_ION] + seg_off[sg], g.nhi + seg_off[sg],
+                                      zero_phi ? nullptr : g.phi_keep + seg_off[sg], seg_len[sg], g.stream);
+                if (e == cudaSuccess && p.phi_heat) {  // raytracing.f90:530: the heating rate is divided by nHI as well
+                    e = launch_finish_phi(p.phi_heat + seg_off[sg], g.nhi + seg_off[sg], nullptr, seg_len[sg], g.stream);
+                    g.last_launches += 1;
+                }
             }
             if (e != cudaSuccess) return fail_cuda("finish_phi_kernel launch", e);
             g.last_launches += 1;
@@ -702,6 +736,9 @@ int asora_device_close(void)
     if (g.nhi) cudaFree(g.nhi);
     if (g.phi_keep) cudaFree(g.phi_keep);
     g.phi_keep = nullptr;
+    if (g.det_lo) cudaFree(g.det_lo);
+    if (g.det_lo_heat) cudaFree(g.det_lo_heat);
+    g.det_lo = g.det_lo_heat = nullptr;
     if (g.grid_scratch) cudaFree(g.grid_scratch);
     if (g.grid_counters) cudaFree(g.grid_counters);
     g.grid_scratch = nullptr;
@@ -776,6 +813,8 @@ int asora_photo_table_to_device(const double* thin_table, const double* thick_ta
     CK(cudaStreamSynchronize(g.stream));
     cudaFree(raw);
     g.ntab = NumTau;
+    g.table_max = 0.0;
+    for (int i = 0; i < NumTau; i++) g.table_max = std::max(g.table_max, std::max(std::fabs(thin_table[i]) * 1e-7, std::fabs(thick_table[i])));
     {
         cudaResourceDesc rd;
         std::memset(&rd, 0, sizeof(rd));
@@ -806,6 +845,8 @@ int asora_heat_table_to_device(const double* heat_thin_table, const double* heat
     if (e != cudaSuccess) return fail_cuda("pair_table_kernel launch", e);
     CK(cudaStreamSynchronize(g.stream));
     cudaFree(raw);
+    for (int i = 0; i < NumTau; i++)
+        g.table_max = std::max(g.table_max, std::max(std::fabs(heat_thin_table[i]) * 1e-7, std::fabs(heat_thick_table[i])));
     g.heat_tables = true;
     return 0;
 }
@@ -888,6 +929,8 @@ int asora_source_data_to_device(const int32_t* pos, const double* flux, int NumS
     CK(cudaMemcpyAsync(g.src_flux_sorted, sflux.data(), sizeof(double) * (size_t)NumSrc, cudaMemcpyHostToDevice, g.stream));
     CK(cudaStreamSynchronize(g.stream));
     g.nsrc = NumSrc;
+    g.flux_max = 0.0;
+    for (int n = 0; n < NumSrc; n++) g.flux_max = std::max(g.flux_max, std::fabs(flux[n]));
     return 0;
 }
 
@@ -1210,6 +1253,12 @@ int64_t asora_plan_export(int N, double R, double dr, int sphere_only, int octan
         if (level_mid) std::copy(plan.level_mid.begin(), plan.level_mid.end(), level_mid);
     }
     return n;
+}
+
+int asora_set_deterministic(int on)
+{
+    g.deterministic = on ? 1 : 0;
+    return 0;
 }
 
 int asora_set_sphere_only(int sphere_only)

@@ -98,6 +98,11 @@ struct SweepParams {
     int src_begin, src_count;
     int sphere_only;          // grid-cooperative variant: skip cells outside the R sphere
     unsigned zface_offset;    // != 0: z-face cells use the (k,i,j)-ordered copies of nhi / phi this many doubles behind them
+    // deterministic accumulation (asora_set_deterministic): phi_ion / phi_heat then hold the high parts and det_lo /
+    // det_lo_heat the low parts of 128-bit fixed-point sums, see deposit_rate in sweep_device.cuh; det_scale == 0: off
+    long long* det_lo;
+    long long* det_lo_heat;
+    double det_scale;         // 2^s: a rate times this is the fixed-point value
     double* coldens_out;      // optional N^3 grid receiving outgoing optical depths (debug) or
                               // the L2-resident scratch of the grid-cooperative variant
 };
@@ -157,6 +162,8 @@ cudaError_t launch_prepare_nhi_transposed(const double* ndens, const double* xh_
                                           int N, cudaStream_t stream);
 cudaError_t launch_finish_phi_transposed(double* phi, const double* phi_t, const double* ntau, const double* keep, int N,
                                          cudaStream_t stream);
+cudaError_t launch_finish_phi_fixed(double* phi_hi, const long long* lo, const double* ntau, const double* keep, double inv_scale,
+                                    int64_t ncell, cudaStream_t stream);
 cudaError_t launch_reverse_axes(const double* in, double* out, int N, cudaStream_t stream);
 cudaError_t launch_scale_grid(double* grid, double factor, int64_t ncell, cudaStream_t stream);
 cudaError_t launch_pair_table(const double* table, double2* pairs, int ntab, cudaStream_t stream);

@@ -560,6 +560,29 @@ __global__ void finish_phi_kernel(double* __restrict__ phi, const double* __rest
     }
 }
 
+// The division pass of a deterministic sweep: sum = (hi * 2^40 + lo) / 2^s from the two integer grids (the high parts sit
+// in the rate grid itself), then as above.
+__global__ void finish_phi_fixed_kernel(double* __restrict__ phi_hi, const long long* __restrict__ lo, const double* __restrict__ ntau,
+                                        const double* __restrict__ keep, double inv_scale, int64_t ncell)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (int64_t)gridDim.x * blockDim.x) {
+        const long long hi = reinterpret_cast<const long long*>(phi_hi)[i];
+        const double sum = ((double)hi * (double)(1ll << ASORA_DET_LOW_BITS) + (double)lo[i]) * inv_scale;
+        double v = (sum != 0.0) ? sum / ntau[i] : 0.0;
+        if (keep) v += keep[i];
+        phi_hi[i] = v;
+    }
+}
+
+cudaError_t launch_finish_phi_fixed(double* phi_hi, const long long* lo, const double* ntau, const double* keep, double inv_scale,
+                                    int64_t ncell, cudaStream_t stream)
+{
+    int64_t blocks = (ncell + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    finish_phi_fixed_kernel<<<(int)blocks, 256, 0, stream>>>(phi_hi, lo, ntau, keep, inv_scale, ncell);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_finish_phi(double* phi, const double* ntau, const double* keep, int64_t ncell, cudaStream_t stream)
 {
     int64_t blocks = (ncell + 255) / 256;

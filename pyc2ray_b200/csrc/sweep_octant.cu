@@ -91,10 +91,10 @@ __device__ __forceinline__ void rate_cells(double (&tin)[NB], double (&tout)[NB]
         // rates.cu:28-38: thick cells absorb T(tau_in) - T(tau_out), thin cells dtau * T_thin(tau_out)
         const double absorbed = thick ? (t_in - t_out) : dtau[u] * t_out;
         const bool deposit = pos[u] != ASORA_NO_DEPOSIT;
-        if (deposit) atomicAdd(p.phi_ion + pos[u], skn[u] * absorbed);  // RED.E.ADD.F64, resolved at L2
+        if (deposit) deposit_rate(p.phi_ion, p.det_lo, p.det_scale, pos[u], skn[u] * absorbed);  // RED at L2
         if (HEAT) {  // photorates.f90:118,124 with the table argument convention of rates.cu:37 (tau_out for thin cells)
             const double heated = thick ? (h_in - h_out) : dtau[u] * h_out;
-            if (deposit) atomicAdd(p.phi_heat + pos[u], skn[u] * heated);
+            if (deposit) deposit_rate(p.phi_heat, p.det_lo_heat, p.det_scale, pos[u], skn[u] * heated);
         }
     }
 }

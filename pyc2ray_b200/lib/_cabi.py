@@ -50,6 +50,7 @@ SIGNATURES = {
     "asora_set_sweep_variant": (_i, [_i]),
     "asora_set_tuning": (_i, [_i, _i]),
     "asora_set_sphere_only": (_i, [_i]),
+    "asora_set_deterministic": (_i, [_i]),
     "asora_set_octant_shape": (_i, [_i, _i, _i, _i]),
     "asora_plan_builds": (_i, []),
     "asora_plan_export": (_i64, [_i, _d, _d, _i, _i, _i, _i64, c_dp, c_dp, ctypes.POINTER(ctypes.c_uint16),
