@@ -203,8 +203,8 @@ int asora_set_sphere_only(int sphere_only);
 /* Deterministic accumulation of the rates.  By default every rated (source, cell) pair adds its rate with one fp64
  * reduction at L2, so phi_ion depends on the arrival order at the 1e-16 level, like the reference's atomicAdd
  * (raytracing.cu:328).  With on != 0 every contribution is split exactly into two integers of a 128-bit fixed-point
- * number (scaled so that the largest possible contribution keeps 42 bits of headroom for the sum, the smallest ones 53
- * significant bits down to 1e-9 of it) and added with two 64-bit integer reductions: integer sums are associative, so
+ * number (scaled so that 2^17 of the largest possible contribution fit a cell and contributions down to 1e-11 of it keep
+ * 53 significant bits) and added with two 64-bit integer reductions: integer sums are associative, so
  * phi_ion is bit-identical from run to run, for every launch shape, split and sweep variant, and for every sharding of
  * the sources that sums the per-rank grids in a fixed order.  Costs a second N^3 grid of 8 bytes per cell and a second
  * reduction per rated cell; the (k,i,j)-ordered z-face copies are not used.  Not available on the single-source debug

@@ -90,7 +90,8 @@ struct Context {
     long long* det_lo = nullptr;      // low parts of the fixed-point sums (N^3), and of the heating sums
     long long* det_lo_heat = nullptr;
     double flux_max = 0.0;            // largest uploaded source flux
-    double table_max = 0.0;           // largest |table entry| (photo and heating tables): bounds one cell's absorbed fraction
+    double table_max = 0.0;           // largest |photo table entry|: bounds one cell's absorbed fraction
+    double heat_table_max = 0.0;      // the same for the heating tables
     // parameters of the last sweep, for the lazily evaluated update count; and a one-entry cache of it
     int last_count = 0;
     double last_R = 0, last_dr = 0;
@@ -348,19 +349,22 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
         p.phi_heat = g.buf[ASORA_BUF_PHI_HEAT];
     }
     p.det_lo = p.det_lo_heat = nullptr;
-    p.det_scale = 0.0;
+    p.det_scale = p.det_scale_heat = 0.0;
     if (g.deterministic) {
         if (coldens_grid) return fail("deterministic accumulation is not available on the single-source debug path");
         // largest possible contribution: strength * kpref * 4 pi (source cell) * (difference of two table entries)
         const double vmax = 2.0 * g.flux_max * p.kpref * ASORA_FOURPI * g.table_max;
         int e2 = 0;
         std::frexp(vmax > 0.0 ? vmax : 1.0, &e2);  // vmax < 2^e2
-        p.det_scale = std::ldexp(1.0, 82 - e2);   // contributions stay below 2^82 = 2^42 high parts of 2^40
+        p.det_scale = std::ldexp(1.0, 88 - e2);   // contributions stay below 2^88 = 2^42 high parts of 2^46
         if (!g.det_lo) CK(cudaMalloc(&g.det_lo, sizeof(long long) * g.ncell));
         p.det_lo = g.det_lo;
         if (p.phi_heat) {
             if (!g.det_lo_heat) CK(cudaMalloc(&g.det_lo_heat, sizeof(long long) * g.ncell));
             p.det_lo_heat = g.det_lo_heat;
+            const double hmax = 2.0 * g.flux_max * p.kpref * ASORA_FOURPI * g.heat_table_max;
+            std::frexp(hmax > 0.0 ? hmax : 1.0, &e2);
+            p.det_scale_heat = std::ldexp(1.0, 88 - e2);
         }
     }
     p.thin = g.thin;
@@ -632,7 +636,7 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
                                             zero_phi ? nullptr : g.phi_keep + seg_off[sg], 1.0 / p.det_scale, seg_len[sg], g.stream);
                 if (e == cudaSuccess && p.phi_heat) {
                     e = launch_finish_phi_fixed(p.phi_heat + seg_off[sg], p.det_lo_heat + seg_off[sg], g.nhi + seg_off[sg], nullptr,
-                                                1.0 / p.det_scale, seg_len[sg], g.stream);
+                                                1.0 / p.det_scale_heat, seg_len[sg], g.stream);
                     g.last_launches += 1;
                 }
             } else {
@@ -845,8 +849,9 @@ int asora_heat_table_to_device(const double* heat_thin_table, const double* heat
     if (e != cudaSuccess) return fail_cuda("pair_table_kernel launch", e);
     CK(cudaStreamSynchronize(g.stream));
     cudaFree(raw);
+    g.heat_table_max = 0.0;
     for (int i = 0; i < NumTau; i++)
-        g.table_max = std::max(g.table_max, std::max(std::fabs(heat_thin_table[i]) * 1e-7, std::fabs(heat_thick_table[i])));
+        g.heat_table_max = std::max(g.heat_table_max, std::max(std::fabs(heat_thin_table[i]) * 1e-7, std::fabs(heat_thick_table[i])));
     g.heat_tables = true;
     return 0;
 }

@@ -103,6 +103,7 @@ struct SweepParams {
     long long* det_lo;
     long long* det_lo_heat;
     double det_scale;         // 2^s: a rate times this is the fixed-point value
+    double det_scale_heat;    // the same for the heating rates (their tables have their own magnitude)
     double* coldens_out;      // optional N^3 grid receiving outgoing optical depths (debug) or
                               // the L2-resident scratch of the grid-cooperative variant
 };

@@ -208,28 +208,28 @@ __device__ __forceinline__ int wrap(int i, int N)
 //   default        RED.E.ADD.F64, resolved at L2: one fire-and-forget fp64 reduction per rated (source, cell) pair; the sum
 //                  depends on the order in which the L2 sees them at the 1e-16 level (like the reference's atomicAdd,
 //                  raytracing.cu:328)
-//   deterministic  (det_scale != 0) the contribution is split exactly into two integers, value * 2^s = hi * 2^40 + lo with
-//                  |lo| < 2^40, and added with two 64-bit integer REDs; integer addition is associative, so the sums --
+//   deterministic  (DET instantiations, asora_set_deterministic) the contribution is split exactly into two integers, value * 2^s = hi * 2^46 + lo with |lo| < 2^46, and added with two 64-bit integer REDs; integer addition is associative, so the sums --
 //                  and phi_ion after the division pass -- are bit-identical from run to run and for every launch shape.
-//                  s is chosen on the host so that the largest possible contribution stays below 2^82 (asora_api.cu),
-//                  i.e. a contribution 1e-9 times that still keeps 53 significant bits.
-#define ASORA_DET_LOW_BITS 40
+//                  s is chosen on the host so that the largest possible contribution stays below 2^88 (asora_api.cu):
+//                  a contribution 1e-11 times that still keeps 53 significant bits, and 2^17 contributions fit a cell.
+#define ASORA_DET_LOW_BITS 46
+template <bool DET>
 __device__ __forceinline__ void deposit_rate(double* __restrict__ grid, long long* __restrict__ lo_grid, double det_scale,
                                              size_t pos, double value)
 {
-    if (det_scale == 0.0) {
+    if (!DET) {
         atomicAdd(grid + pos, value);
     } else {
         const double v = value * det_scale;                                        // exact: a power of two
         const long long hi = __double2ll_rz(v * (1.0 / (double)(1ll << ASORA_DET_LOW_BITS)));
-        const double rest = v - (double)hi * (double)(1ll << ASORA_DET_LOW_BITS);  // exact, |rest| < 2^40
+        const double rest = v - (double)hi * (double)(1ll << ASORA_DET_LOW_BITS);  // exact, |rest| < 2^46
         atomicAdd(reinterpret_cast<unsigned long long*>(grid) + pos, (unsigned long long)hi);
         atomicAdd(reinterpret_cast<unsigned long long*>(lo_grid) + pos, (unsigned long long)__double2ll_rz(rest));
     }
 }
 
 // skn = strength * kpref * inv_np.
-template <int REP, bool TEX, bool HEAT>
+template <int REP, bool TEX, bool HEAT, bool DET = false>
 __device__ __forceinline__ double finish_cell_pre(double tau_in, double path_cells, double skn, unsigned flags,
                                                   double ntau_p, size_t pos, const SweepParams& p,
                                                   const double2* __restrict__ log2_tab)
@@ -242,19 +242,19 @@ __device__ __forceinline__ double finish_cell_pre(double tau_in, double path_cel
         photo_lookup2<REP, TEX, HEAT>(thick, tau_in, tau_out, p, log2_tab, t_in, t_out, h_in, h_out);
         // rates.cu:28-38: thick cells absorb T(tau_in) - T(tau_out), thin cells dtau * T_thin(tau_out)
         const double absorbed = thick ? (t_in - t_out) : dtau * t_out;
-        deposit_rate(p.phi_ion, p.det_lo, p.det_scale, pos, skn * absorbed);
+        deposit_rate<DET>(p.phi_ion, p.det_lo, p.det_scale, pos, skn * absorbed);
         if (HEAT) {  // photorates.f90:118,124 + raytracing.f90:530,537, same prefactor and the same deferred / nHI
             const double heated = thick ? (h_in - h_out) : dtau * h_out;
-            deposit_rate(p.phi_heat, p.det_lo_heat, p.det_scale, pos, skn * heated);
+            deposit_rate<DET>(p.phi_heat, p.det_lo_heat, p.det_scale_heat, pos, skn * heated);
         }
     }
     return tau_out;
 }
 
-template <int REP, bool TEX, bool HEAT>
+template <int REP, bool TEX, bool HEAT, bool DET = false>
 __device__ __forceinline__ double finish_cell(double tau_in, double path_cells, double inv_np, unsigned flags,
                                               double ntau_p, double sk, size_t pos, const SweepParams& p,
                                               const double2* __restrict__ log2_tab)
 {
-    return finish_cell_pre<REP, TEX, HEAT>(tau_in, path_cells, sk * inv_np, flags, ntau_p, pos, p, log2_tab);
+    return finish_cell_pre<REP, TEX, HEAT, DET>(tau_in, path_cells, sk * inv_np, flags, ntau_p, pos, p, log2_tab);
 }

@@ -123,7 +123,7 @@ __device__ __forceinline__ void fetch_cell(Fetched<S>& f, const int4* __restrict
 }
 
 // One level of the sweep for the S sources of a CTA.
-template <int S, int BLOCK, int REP, bool DIAG, bool CDOUT, bool TEX, bool PF, bool HEAT, bool ZF>
+template <int S, int BLOCK, int REP, bool DIAG, bool CDOUT, bool TEX, bool PF, bool HEAT, bool ZF, bool DET>
 __device__ __forceinline__ void sweep_level(const int4* __restrict__ plan, const unsigned* __restrict__ dwords, int ncells,
                                             int beg, int end, int m, double* __restrict__ cur,
                                             const double* __restrict__ prev, int max_level_cells,
@@ -146,7 +146,7 @@ __device__ __forceinline__ void sweep_level(const int4* __restrict__ plan, const
             if (!live[s]) continue;
             const double* pv = prev + s * max_level_cells;
             const double cin = interp_coldens<false, DIAG>(pv[c.nb1], pv[c.nb2], pv[c.nb3], pv[c.nb4], c.wA, c.wB, c.flags);
-            const double cdho = finish_cell<REP, TEX, HEAT>(cin, c.path, c.inv_np, c.flags, c.nhi[s], sk[s], c.pos[s], p, log2_tab);
+            const double cdho = finish_cell<REP, TEX, HEAT, DET>(cin, c.path, c.inv_np, c.flags, c.nhi[s], sk[s], c.pos[s], p, log2_tab);
             cur[s * max_level_cells + slot] = cdho;
             if (CDOUT) p.coldens_out[c.pos[s]] = cdho;
         }
@@ -161,7 +161,7 @@ __device__ __forceinline__ void sweep_level(const int4* __restrict__ plan, const
 // 64 registers (-10...-40 %, spills), prefetch.global.L1 of the next plan entry (-4 %), a split arrive/wait level
 // barrier (-12 %), the plan staged through shared memory by per-warp bulk copies (-19 %: fewer stalls, but 20 %
 // more instructions).  What is kept: the 4-byte offsets word one cell ahead (PF) where registers allow it.
-template <int S, int BLOCK, int MINB, int REP, bool CDOUT, bool TEX, bool PF, bool HEAT, bool ZF>
+template <int S, int BLOCK, int MINB, int REP, bool CDOUT, bool TEX, bool PF, bool HEAT, bool ZF, bool DET>
 __global__ void __launch_bounds__(BLOCK, MINB)
 sweep_smem_kernel(const int4* __restrict__ plan, const unsigned* __restrict__ dwords, int ncells,
                   const int* __restrict__ level_start_all,
@@ -183,8 +183,8 @@ sweep_smem_kernel(const int4* __restrict__ plan, const unsigned* __restrict__ dw
 
     for (int t = threadIdx.x; t < 256 * REP; t += BLOCK) log2_all[t] = __ldg(p.log2_tab + t / REP);
     const double2* log2_tab = log2_all + (REP > 1 ? (threadIdx.x & (REP - 1)) : 0);
-    // the source cell "interpolates" slot 0 of the (empty) previous level with weight 1: seed it with 0
-    if (threadIdx.x < S) sh_cd[(size_t)S * max_level_cells + threadIdx.x * max_level_cells] = 0.0;
+    // the zero slot (last of every level buffer, sweep_plan.cu: resolve_zero_slot): zero-weight corners and the source cell
+    if (threadIdx.x < 2 * S) sh_cd[(size_t)(threadIdx.x + 1) * max_level_cells - 1] = 0.0;
 
     int i0[S], j0[S], k0[S];
     double sk[S];
@@ -219,10 +219,10 @@ sweep_smem_kernel(const int4* __restrict__ plan, const unsigned* __restrict__ dw
         double* cur = sh_cd + (size_t)(m & 1) * S * max_level_cells;
         const double* prev = sh_cd + (size_t)((m & 1) ^ 1) * S * max_level_cells;
         if (m < 2)
-            sweep_level<S, BLOCK, REP, true, CDOUT, TEX, PF, HEAT, ZF>(plan, dwords, ncells, beg, end, m, cur, prev, max_level_cells,
+            sweep_level<S, BLOCK, REP, true, CDOUT, TEX, PF, HEAT, ZF, DET>(plan, dwords, ncells, beg, end, m, cur, prev, max_level_cells,
                                                              wrap_tab, side, sk, live, p, log2_tab);
         else
-            sweep_level<S, BLOCK, REP, false, CDOUT, TEX, PF, HEAT, ZF>(plan, dwords, ncells, beg, end, m, cur, prev, max_level_cells,
+            sweep_level<S, BLOCK, REP, false, CDOUT, TEX, PF, HEAT, ZF, DET>(plan, dwords, ncells, beg, end, m, cur, prev, max_level_cells,
                                                               wrap_tab, side, sk, live, p, log2_tab);
         __syncthreads();
         beg = end;
@@ -236,12 +236,12 @@ size_t sweep_smem_bytes(const SweepPlan& plan, int S, int rep)
            (size_t)2 * 3 * S * plan.side * sizeof(unsigned) + (size_t)(plan.nlevels + 1) * sizeof(int);
 }
 
-template <int S, int BLOCK, int MINB, int REP, bool CDOUT, bool TEX, bool PF, bool HEAT = false, bool ZF = false>
+template <int S, int BLOCK, int MINB, int REP, bool CDOUT, bool TEX, bool PF, bool HEAT = false, bool ZF = false, bool DET = false>
 static cudaError_t launch_smem_t(const SweepPlan& plan, const SweepParams& p, cudaStream_t stream)
 {
     const size_t smem = sweep_smem_bytes(plan, S, REP);
     const int grid = ((p.src_count + S - 1) / S) * plan.parts;
-    auto kernel = sweep_smem_kernel<S, BLOCK, MINB, REP, CDOUT, TEX, PF, HEAT, ZF>;
+    auto kernel = sweep_smem_kernel<S, BLOCK, MINB, REP, CDOUT, TEX, PF, HEAT, ZF, DET>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kernel<<<grid, BLOCK, smem, stream>>>(plan.d_cells, plan.d_dwords, (int)plan.ncells, plan.d_level_start, plan.nlevels,
@@ -253,6 +253,10 @@ template <int S, int BLOCK, int MINB>
 static cudaError_t launch_smem_opts(const SweepPlan& plan, const SweepParams& p, int opts, cudaStream_t stream)
 {
     if (p.coldens_out) return launch_smem_t<S, BLOCK, MINB, 1, true, false, false>(plan, p, stream);  // debug path
+    if (p.det_lo) {  // deterministic accumulation: one option set per shape (no z-face copies)
+        if (p.phi_heat) return launch_smem_t<S, BLOCK, MINB, 1, false, true, false, true, false, true>(plan, p, stream);
+        return launch_smem_t<S, BLOCK, MINB, 1, false, true, false, false, false, true>(plan, p, stream);
+    }
     if (p.zface_offset) {  // z-face cells through the (k,i,j)-ordered copies: the one-CTA-per-SM shapes only
         if constexpr (S == 1 && BLOCK >= 768) {
             if (p.phi_heat) return launch_smem_t<S, BLOCK, MINB, 1, false, true, true, true, true>(plan, p, stream);
@@ -370,7 +374,7 @@ __device__ __forceinline__ void group_barrier(unsigned* counter, unsigned nctas,
 // The grid is split into `ngroups` groups of `group_ctas` CTAs; group g sweeps sources g, g+ngroups, ...
 // through its own N^3 scratch grid, so that sources whose levels are much narrower than the GPU run
 // side by side.  ngroups == 1 is "the whole GPU per source".
-template <bool HEAT>
+template <bool HEAT, bool DET>
 __global__ void __launch_bounds__(512, 2)
 sweep_grid_kernel(SweepParams p, int nlevels, int ngroups, int group_ctas, unsigned* counters)
 {
@@ -464,7 +468,7 @@ sweep_grid_kernel(SweepParams p, int nlevels, int ngroups, int group_ctas, unsig
                     const double c4 = ((1.0 - wA) * (1.0 - wB) != 0.0) ? __ldcg(slab + q4) : 0.0;
                     cin = interp_coldens<true, true>(c1, c2, c3, c4, wA, wB, flags);
                 }
-                const double cdho = finish_cell<1, false, HEAT>(cin, path, inv_np, flags, nHI_p, sk, pos, p, log2_tab);
+                const double cdho = finish_cell<1, false, HEAT, DET>(cin, path, inv_np, flags, nHI_p, sk, pos, p, log2_tab);
                 __stcg(slab + pos, cdho);
             }
             group_barrier(counter, (unsigned)group_ctas, epoch);
@@ -484,7 +488,7 @@ int sweep_grid_groups(const SweepParams& p, int max_groups, int* total_ctas_out,
         int dev = 0, sms = 0, per_sm = 0;
         if (cudaGetDevice(&dev) != cudaSuccess) return 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_grid_kernel<true>, block, 0) != cudaSuccess) return 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_grid_kernel<true, true>, block, 0) != cudaSuccess) return 0;
         if (per_sm < 1) return 0;
         total_cached = sms * per_sm;
     }
@@ -518,7 +522,8 @@ cudaError_t launch_sweep_grid(const SweepParams& p, int ngroups, unsigned* count
     SweepParams pc = p;
     void* args[] = {(void*)&pc, (void*)&nlevels, (void*)&ngroups, (void*)&group_ctas, (void*)&counters};
     if (launches) *launches += 1;
-    void* kernel = pc.phi_heat ? (void*)sweep_grid_kernel<true> : (void*)sweep_grid_kernel<false>;
+    void* kernel = pc.det_lo ? (pc.phi_heat ? (void*)sweep_grid_kernel<true, true> : (void*)sweep_grid_kernel<false, true>)
+                             : (pc.phi_heat ? (void*)sweep_grid_kernel<true, false> : (void*)sweep_grid_kernel<false, false>);
     return cudaLaunchCooperativeKernel(kernel, dim3(total), dim3(block), args, 0, stream);
 }
 
@@ -560,7 +565,7 @@ __global__ void finish_phi_kernel(double* __restrict__ phi, const double* __rest
     }
 }
 
-// The division pass of a deterministic sweep: sum = (hi * 2^40 + lo) / 2^s from the two integer grids (the high parts sit
+// The division pass of a deterministic sweep: sum = (hi * 2^46 + lo) / 2^s from the two integer grids (the high parts sit
 // in the rate grid itself), then as above.
 __global__ void finish_phi_fixed_kernel(double* __restrict__ phi_hi, const long long* __restrict__ lo, const double* __restrict__ ntau,
                                         const double* __restrict__ keep, double inv_scale, int64_t ncell)

@@ -41,7 +41,7 @@ namespace {
 
 // Phase 2 for NB cells side by side: rates.cu:16-41 + the deposit of raytracing.cu:324-329 (finish_cell_pre in
 // sweep_device.cuh is the one-cell form).  pos[u] == ASORA_NO_DEPOSIT: nothing to deposit for that cell.
-template <int NB, int REP, bool TEX, bool HEAT>
+template <int NB, int REP, bool TEX, bool HEAT, bool DET>
 __device__ __forceinline__ void rate_cells(double (&tin)[NB], double (&tout)[NB], const double (&skn)[NB], const unsigned (&pos)[NB],
                                            const SweepParams& p, const double2* __restrict__ log2_tab)
 {
@@ -91,10 +91,10 @@ __device__ __forceinline__ void rate_cells(double (&tin)[NB], double (&tout)[NB]
         // rates.cu:28-38: thick cells absorb T(tau_in) - T(tau_out), thin cells dtau * T_thin(tau_out)
         const double absorbed = thick ? (t_in - t_out) : dtau[u] * t_out;
         const bool deposit = pos[u] != ASORA_NO_DEPOSIT;
-        if (deposit) deposit_rate(p.phi_ion, p.det_lo, p.det_scale, pos[u], skn[u] * absorbed);  // RED at L2
+        if (deposit) deposit_rate<DET>(p.phi_ion, p.det_lo, p.det_scale, pos[u], skn[u] * absorbed);  // RED at L2
         if (HEAT) {  // photorates.f90:118,124 with the table argument convention of rates.cu:37 (tau_out for thin cells)
             const double heated = thick ? (h_in - h_out) : dtau[u] * h_out;
-            if (deposit) deposit_rate(p.phi_heat, p.det_lo_heat, p.det_scale, pos[u], skn[u] * heated);
+            if (deposit) deposit_rate<DET>(p.phi_heat, p.det_lo_heat, p.det_scale_heat, pos[u], skn[u] * heated);
         }
     }
 }
@@ -105,7 +105,7 @@ __device__ __forceinline__ void rate_cells(double (&tin)[NB], double (&tout)[NB]
 //            bits); every result is stored for the image across that plane as well
 //   BATCH:   images evaluated side by side, NIMG / BATCH rounds: the straight-line code of a round keeps ~30 registers
 //            per image live, so the batch is what fits the register budget of the launch shape
-template <int NIMG, int BATCH, int OPT, bool CLASS_B, int REP, bool DIAG, bool TEX, bool HEAT>
+template <int NIMG, int BATCH, int OPT, bool CLASS_B, int REP, bool DIAG, bool TEX, bool HEAT, bool DET>
 __device__ __forceinline__ void entry_images(const int4 ra, const int4 rb, double md, double inv_m, int slot, int lmax,
                                              int obase /* first local octant of this thread */, int gbase /* the same, global */,
                                              const unsigned (&X)[2], const unsigned (&Y)[2], const unsigned (&Z)[2],
@@ -198,12 +198,12 @@ __device__ __forceinline__ void entry_images(const int4 ra, const int4 rb, doubl
             double sk_n[NB];
 #pragma unroll
             for (int u = 0; u < NB; u++) sk_n[u] = skn;
-            rate_cells<NB, REP, TEX, HEAT>(tin, tout, sk_n, pos, p, log2_tab);
+            rate_cells<NB, REP, TEX, HEAT, DET>(tin, tout, sk_n, pos, p, log2_tab);
         }
     }  // rounds
 }
 
-template <int BLOCK, int NOCT, int OPT, int BATCH, int REP, bool DIAG, bool TEX, bool HEAT, bool ZF, bool PF>
+template <int BLOCK, int NOCT, int OPT, int BATCH, int REP, bool DIAG, bool TEX, bool HEAT, bool ZF, bool PF, bool DET>
 __device__ __forceinline__ void octant_level(const int4* __restrict__ plan, int ncells, int beg, int mid, int end, double md,
                                              double inv_m, double* __restrict__ cur, const double* __restrict__ prev, int lmax,
                                              const unsigned* __restrict__ wrap_tab, int hi, int part, double sk,
@@ -261,17 +261,17 @@ __device__ __forceinline__ void octant_level(const int4* __restrict__ plan, int 
             Z[0] = Z[1] = w[2 * side + (fz ? hi - dk : hi + dk)];
         }
         if (OPT < 2 || e < mid)
-            entry_images<OPT, BATCH, OPT, false, REP, DIAG, TEX, HEAT>(ra, rb, md, inv_m, e - beg, lmax, obase, gbase, X, Y, Z, cur, prev, sk,
+            entry_images<OPT, BATCH, OPT, false, REP, DIAG, TEX, HEAT, DET>(ra, rb, md, inv_m, e - beg, lmax, obase, gbase, X, Y, Z, cur, prev, sk,
                                                                         p, log2_tab);
         else
-            entry_images<(OPT >= 2 ? OPT / 2 : 1), BATCH, OPT, true, REP, DIAG, TEX, HEAT>(ra, rb, md, inv_m, e - beg, lmax, obase, gbase, X,
+            entry_images<(OPT >= 2 ? OPT / 2 : 1), BATCH, OPT, true, REP, DIAG, TEX, HEAT, DET>(ra, rb, md, inv_m, e - beg, lmax, obase, gbase, X,
                                                                                            Y, Z, cur, prev, sk, p, log2_tab);
     }
 }
 
 // One CTA per (source, group of NOCT octants).  level_bounds_g: [nlevels + 1] level starts, then [3][nlevels] class
 // boundaries for OPT = 8, 4, 2 (build_octant_plan).  dedup == 0: every entry is treated as class A (profiling).
-template <int BLOCK, int MINB, int NOCT, int OPT, int BATCH, int REP, bool TEX, bool HEAT, bool ZF, bool PF>
+template <int BLOCK, int MINB, int NOCT, int OPT, int BATCH, int REP, bool TEX, bool HEAT, bool ZF, bool PF, bool DET>
 __global__ void __launch_bounds__(BLOCK, MINB)
 sweep_octant_kernel(const int4* __restrict__ plan, int ncells, const int* __restrict__ level_bounds_g, int nlevels, int lmax,
                     int hi, int dedup, SweepParams p)
@@ -300,8 +300,8 @@ sweep_octant_kernel(const int4* __restrict__ plan, int ncells, const int* __rest
     }
     for (int t = threadIdx.x; t < 256 * REP; t += BLOCK) log2_all[t] = __ldg(p.log2_tab + t / REP);
     const double2* log2_tab = log2_all + (REP > 1 ? (threadIdx.x & (REP - 1)) : 0);
-    // the source cell "interpolates" slot 0 of the (empty) previous level with weight 1: seed it with 0
-    if (threadIdx.x < NOCT) sh_cd[(size_t)NOCT * lmax + threadIdx.x * lmax] = 0.0;
+    // the zero slot (last of every level buffer, sweep_plan.cu: resolve_zero_slot): zero-weight corners and the source cell
+    if (threadIdx.x < 2 * NOCT) sh_cd[(size_t)(threadIdx.x + 1) * lmax - 1] = 0.0;
     const int i0 = p.src_pos[3 * ns + 0], j0 = p.src_pos[3 * ns + 1], k0 = p.src_pos[3 * ns + 2];
     const double sk = p.src_flux[ns] * p.kpref;
     for (int t = threadIdx.x; t < 3 * side; t += BLOCK) {
@@ -323,10 +323,10 @@ sweep_octant_kernel(const int4* __restrict__ plan, int ncells, const int* __rest
         const double* prev = sh_cd + (size_t)((m & 1) ^ 1) * NOCT * lmax;
         const double md = (double)m, inv_m = inv_level[m];
         if (m < 2)  // the source cell and its 26 neighbours: the only cells with diagonal factors (raytracing.cu:431-441)
-            octant_level<BLOCK, NOCT, OPT, BATCH, REP, true, TEX, HEAT, ZF, PF>(plan, ncells, beg, mid, end, md, inv_m, cur, prev, lmax,
+            octant_level<BLOCK, NOCT, OPT, BATCH, REP, true, TEX, HEAT, ZF, PF, DET>(plan, ncells, beg, mid, end, md, inv_m, cur, prev, lmax,
                                                                                 wrap_tab, hi, part, sk, p, log2_tab);
         else
-            octant_level<BLOCK, NOCT, OPT, BATCH, REP, false, TEX, HEAT, ZF, PF>(plan, ncells, beg, mid, end, md, inv_m, cur, prev, lmax,
+            octant_level<BLOCK, NOCT, OPT, BATCH, REP, false, TEX, HEAT, ZF, PF, DET>(plan, ncells, beg, mid, end, md, inv_m, cur, prev, lmax,
                                                                                  wrap_tab, hi, part, sk, p, log2_tab);
         __syncthreads();
         beg = end;
@@ -334,12 +334,12 @@ sweep_octant_kernel(const int4* __restrict__ plan, int ncells, const int* __rest
     }
 }
 
-template <int BLOCK, int MINB, int NOCT, int OPT, int BATCH, int REP, bool TEX, bool HEAT, bool ZF, bool PF>
+template <int BLOCK, int MINB, int NOCT, int OPT, int BATCH, int REP, bool TEX, bool HEAT, bool ZF, bool PF, bool DET = false>
 cudaError_t launch_t(const SweepPlan& plan, const SweepParams& p, int dedup, cudaStream_t stream)
 {
     const size_t smem = sweep_octant_smem_bytes(plan, NOCT, REP, ZF);
     const int grid = p.src_count * (8 / NOCT);
-    auto kernel = sweep_octant_kernel<BLOCK, MINB, NOCT, OPT, BATCH, REP, TEX, HEAT, ZF, PF>;
+    auto kernel = sweep_octant_kernel<BLOCK, MINB, NOCT, OPT, BATCH, REP, TEX, HEAT, ZF, PF, DET>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kernel<<<grid, BLOCK, smem, stream>>>(plan.d_cells, (int)plan.ncells, plan.d_level_start, plan.nlevels, plan.max_level_cells,
@@ -353,6 +353,10 @@ template <int BLOCK, int MINB, int NOCT, int OPT, int BATCH, bool BIG>
 cudaError_t launch_opts(const SweepPlan& plan, const SweepParams& p, int opts, cudaStream_t stream)
 {
     const int dedup = (opts & 8) ? 0 : 1;
+    if (p.det_lo) {  // deterministic accumulation: one option set per shape
+        if (p.zface_offset || p.phi_heat) return cudaErrorInvalidValue;
+        return launch_t<BLOCK, MINB, NOCT, OPT, BATCH, 1, true, false, false, false, true>(plan, p, dedup, stream);
+    }
     if (p.phi_heat) {
         if (p.zface_offset) return cudaErrorInvalidValue;  // heating sweeps do not use the z-face copies
         return launch_t<BLOCK, MINB, NOCT, OPT, BATCH, 1, true, true, false, false>(plan, p, dedup, stream);

@@ -71,6 +71,20 @@ int64_t asora_count_rated_cells(int N, double R, double dr)
     return cnt;
 }
 
+// Upstream corners whose bilinear weight is exactly zero (SURVEY note N3) are pointed at a reserved slot behind the last
+// cell of the largest level, which the kernels keep at 0: the weights are formed as products over the other corners'
+// max(0.6, tau) (interp_weighted), so whatever a zero-weight corner holds cancels only mathematically, not bit for bit --
+// a fixed 0 makes a cell's optical depth independent of how the sweep is split and enumerated (deterministic mode).
+// The source cell "interpolates" that slot with weight 1.  Returns the buffer length per level: largest level + 1.
+static const int kZeroSlot = 0xffff;
+static int resolve_zero_slot(std::vector<PlanCell>& cells, int maxc)
+{
+    for (PlanCell& c : cells)
+        for (int t = 0; t < 4; t++)
+            if (c.nb[t] == kZeroSlot) c.nb[t] = (uint16_t)maxc;
+    return maxc + 1;
+}
+
 // Device copy of plan.cells as two 16-byte streams + the 4-byte offsets stream, and the level bounds.
 static bool upload_plan(SweepPlan& plan, std::string& err)
 {
@@ -189,7 +203,7 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_o
             ls[m + 1] = ls[m] + count[m];
             maxc = std::max(maxc, count[m]);
         }
-        if (maxc > 65535) {
+        if (maxc > 65533) {
             err = "sweep plan: level too large for 16-bit slots";
             return false;
         }
@@ -208,11 +222,10 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_o
                     pc.d[2] = (uint8_t)(k - lo);
                     pc.ab = 0;
                     pc.flags = 0;
-                    pc.nb[0] = pc.nb[1] = pc.nb[2] = pc.nb[3] = 0;
+                    pc.nb[0] = pc.nb[1] = pc.nb[2] = pc.nb[3] = kZeroSlot;
                     if (m == 0) {
                         // source cell: no incoming column, path dr/2, volume dr^3 (raytracing.cu:285-294).
-                        // wA = wB = 0 makes it "interpolate" slot 0 of the previous buffer with weight 1;
-                        // the kernel seeds that slot with 0.
+                        // wA = wB = 0 makes it "interpolate" the zero slot with weight 1.
                         pc.flags = PC_SOURCE | (owned ? PC_RATED : 0u);
                         pc.wA = pc.wB = 0.0;
                         pc.path = 0.5;
@@ -254,12 +267,12 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_o
                         if (c == 1 && (a == 1 || b == 1)) pc.flags |= (a == 1 && b == 1) ? PC_DIAG3 : PC_DIAG2;
                         if (owned && rated(i, j, k)) pc.flags |= PC_RATED;
                         if (ka == m && ja < m && ia < m) pc.flags |= PC_ZFACE;
-                        // upstream slots; zero-weight corners may fall outside the part -> slot 0, weight 0
+                        // upstream slots; zero-weight corners (which may fall outside the part) -> the zero slot
                         const double s[4] = {pc.wA * pc.wB, pc.wB * (1.0 - pc.wA), pc.wA * (1.0 - pc.wB),
                                              (1.0 - pc.wA) * (1.0 - pc.wB)};
                         int* nn[4] = {n1, n2, n3, n4};
                         for (int t = 0; t < 4; t++) {
-                            int sl = 0;
+                            int sl = kZeroSlot;
                             if (s[t] != 0.0) {
                                 const int* q = nn[t];
                                 const bool in = q[0] >= lo && q[0] <= hi && q[1] >= lo && q[1] <= hi && q[2] >= lo && q[2] <= hi;
@@ -281,7 +294,7 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_o
     plan.dr = dr;
     plan.q_max = Q;
     plan.nlevels = nlevels;
-    plan.max_level_cells = maxc;
+    plan.max_level_cells = resolve_zero_slot(plan.cells, maxc);
     plan.lo = lo;
     plan.side = side;
     plan.sphere_only = sphere_only;
@@ -375,7 +388,7 @@ bool build_octant_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_
         plan.level_mid[(size_t)1 * nlevels + m] = plan.level_start[m] + gstart[(size_t)m * 16 + 4];   // OPT = 4
         plan.level_mid[(size_t)2 * nlevels + m] = plan.level_start[m] + gstart[(size_t)m * 16 + 8];   // OPT = 2
     }
-    if (maxc > 65535) {
+    if (maxc > 65533) {
         err = "octant plan: level too large for 16-bit slots";
         return false;
     }
@@ -403,7 +416,7 @@ bool build_octant_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_
                 pc.d[2] = (uint8_t)k;
                 pc.ab = 0;
                 pc.flags = (uint8_t)(zmask_of(i, j, k) << 5);
-                pc.nb[0] = pc.nb[1] = pc.nb[2] = pc.nb[3] = 0;
+                pc.nb[0] = pc.nb[1] = pc.nb[2] = pc.nb[3] = kZeroSlot;
                 if (m == 0) {  // source cell (raytracing.cu:285-294), see build_sweep_plan
                     pc.flags |= PC_SOURCE | PC_RATED;
                     pc.wA = pc.wB = 0.0;
@@ -447,7 +460,7 @@ bool build_octant_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_
                                          (1.0 - pc.wA) * (1.0 - pc.wB)};
                     int* nn[4] = {n1, n2, n3, n4};
                     for (int t = 0; t < 4; t++) {
-                        int sl = 0;
+                        int sl = kZeroSlot;
                         if (s[t] != 0.0) {
                             const int* q = nn[t];
                             const bool in = q[0] >= 0 && q[1] >= 0 && q[2] >= 0 && q[0] <= hi && q[1] <= hi && q[2] <= hi;
@@ -468,7 +481,7 @@ bool build_octant_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_
     plan.dr = dr;
     plan.q_max = Q;
     plan.nlevels = nlevels;
-    plan.max_level_cells = maxc;
+    plan.max_level_cells = resolve_zero_slot(plan.cells, maxc);
     plan.lo = -hi;
     plan.side = 2 * hi + 1;
     plan.sphere_only = sphere_only;

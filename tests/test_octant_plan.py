@@ -71,7 +71,7 @@ def emulate(plan, c, noct, opt, dedup):
         strength = c["flux_flat"][s]
         for part in range(parts):
             bufs = np.full((2, noct, lmax), np.nan)
-            bufs[1, :, 0] = 0.0
+            bufs[:, :, lmax - 1] = 0.0   # the zero slot: zero-weight corners and the source cell
             for m in range(plan["nlevels"]):
                 beg, end = plan["level_start"][m], plan["level_start"][m + 1]
                 mid = plan["level_mid"][row][m] if (dedup and opt >= 2) else end
