@@ -188,7 +188,9 @@ int asora_debug_single_source(double R, double sig, double dr, const double* xh_
 
 /* Force the sweep variant: 0 = automatic, 1 = shared-memory level sweep (one CTA per source batch, one cell per
  * thread), 2 = grid-cooperative level sweep (whole GPU per source), 3 = mirror-image sweep (one plan entry and up to
- * eight octant images per thread; needs a mirror-symmetric cell set, i.e. q_max <= N/2 - 1 on even meshes).
+ * eight octant images per thread; needs a mirror-symmetric cell set, i.e. q_max <= N/2 - 1 on even meshes),
+ * 4 = large-radius sweep (one thread-block cluster per wedge of a source, level buffers in distributed shared memory).
+ * Automatic: 3 or 1 while two levels of a source fit the shared memory of a CTA, else 4, else 2.
  * Returns non-zero for unknown values. */
 int asora_set_sweep_variant(int variant);
 
@@ -226,6 +228,10 @@ int asora_set_tuning(int sources_per_cta, int block_threads);
  * automatic choice, 8 = no de-duplication of plane cells; probe builds add 4 and 16 (see launch_opts).  For tuning
  * and profiling. */
 int asora_set_octant_shape(int octants_per_cta, int images_per_thread, int batch, int block_threads);
+
+/* Override the launch shape of the large-radius sweep (variant 4): CTAs per cluster (1, 2, 4, 8) and threads per CTA
+ * (256, 384 or 512 for clusters of 8; 256 or 512 otherwise); 0 = automatic.  For tuning and profiling. */
+int asora_set_cluster_shape(int ctas_per_cluster, int block_threads);
 
 /* Number of sweep plans built since the library was loaded (the plans are cached per mesh, radius, cell size and
  * split; tests use this to check that repeated sweeps do not rebuild them). */

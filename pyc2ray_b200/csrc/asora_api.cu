@@ -84,6 +84,7 @@ struct Context {
     int tune_parts = 0;
     int oct_noct = 0, oct_opt = 0, oct_batch = 0, oct_block = 0;  // forced shape of the mirror-image sweep (0 = automatic)
     int oct_opts = 0;                                              // its profiling knobs
+    int clu_logc = 0, clu_block = 0;  // forced cluster size (log2) and threads of the large-radius sweep (0 = automatic)
     int slab_begin = 0, slab_count = 0;  // active planes of a slab-decomposed run (0 = whole grid)
     int sphere_only = 0;
     int deterministic = 0;            // asora_set_deterministic: fixed-point accumulation of the rates
@@ -505,7 +506,21 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
             }
         }
         if (variant == 1 && !plan) return fail("sweep variant 1 forced but a level does not fit in shared memory");
-        if (variant == 0) variant = plan ? 1 : 2;
+        if (variant == 0) variant = plan ? 1 : 4;
+    }
+    // Large radii: one cluster per wedge with the level buffers in distributed shared memory (variant 4) while a CTA's
+    // share of two levels fits its shared memory (up to ~1000^3 meshes with clusters of 8), else the grid-cooperative
+    // sweep through L2 scratch grids (variant 2).
+    int clu_logc = 3, clu_block = 256;
+    if (variant == 4) {
+        p.sphere_only = sphere_only ? 1 : 0;
+        const int nl = sweep_cluster_levels(p);
+        if (g.clu_logc > 0) clu_logc = g.clu_logc - 1;
+        if (g.clu_block > 0) clu_block = g.clu_block;
+        if (sweep_cluster_smem_bytes(nl, clu_logc) > budget) {
+            if (g.variant_forced == 4) return fail("sweep variant 4 forced but a level does not fit the cluster's shared memory");
+            variant = 2;
+        }
     }
 
     // host-side preparation of the grid-cooperative sweep (kept outside the timed region)
@@ -596,6 +611,9 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
         g.last_levels = plan->nlevels;
         cudaError_t e = launch_sweep_smem(*plan, p, S, block, opts, g.stream, &g.last_launches);
         if (e != cudaSuccess) return fail_cuda("sweep_smem_kernel launch", e);
+    } else if (variant == 4) {
+        cudaError_t e = launch_sweep_cluster(p, clu_logc, clu_block, g.stream, &g.last_launches, &g.last_levels);
+        if (e != cudaSuccess) return fail_cuda("sweep_wedge_kernel launch", e);
     } else if (variant == 3) {
         g.last_levels = plan->nlevels;
         if (p.zface_offset && sweep_octant_smem_bytes(*plan, noct, (opts & 1) ? 8 : 1, true) > budget) opts &= ~1;
@@ -1199,7 +1217,7 @@ int asora_invalidate_temperature(void)
 
 int asora_set_sweep_variant(int variant)
 {
-    if (variant < 0 || variant > 3) return fail("set_sweep_variant: unknown variant");
+    if (variant < 0 || variant > 4) return fail("set_sweep_variant: unknown variant");
     g.variant_forced = variant;
     return 0;
 }
@@ -1215,6 +1233,20 @@ int asora_set_octant_shape(int octants_per_cta, int images_per_thread, int batch
     g.oct_batch = batch;
     g.oct_opts = (block_threads >> 16) & 0xff;
     g.oct_block = block_threads & 0xffff;
+    return 0;
+}
+
+int asora_set_cluster_shape(int ctas_per_cluster, int block_threads)
+{
+    int logc = 0;
+    if (ctas_per_cluster != 0) {
+        if (!(ctas_per_cluster == 1 || ctas_per_cluster == 2 || ctas_per_cluster == 4 || ctas_per_cluster == 8))
+            return fail("set_cluster_shape: CTAs per cluster must be 1, 2, 4 or 8");
+        while ((1 << logc) < ctas_per_cluster) logc++;
+        logc += 1;  // stored biased by one: 0 = automatic
+    }
+    g.clu_logc = logc;
+    g.clu_block = block_threads;
     return 0;
 }
 

@@ -152,6 +152,10 @@ size_t sweep_octant_smem_bytes(const SweepPlan& plan, int noct, int log2_copies,
 cudaError_t launch_sweep_octant(const SweepPlan& plan, const SweepParams& p, int noct, int opt, int batch, int block, int opts,
                                 cudaStream_t stream, int* launches);
 int sweep_octant_shape_ok(int noct, int opt, int batch, int block);  // 0 no, 1 yes, 2 yes incl. z-face copies
+// sweep_cluster.cu: the large-radius sweep, one cluster of 2^logc CTAs per wedge of a source (24 wedges per source)
+int sweep_cluster_levels(const SweepParams& p);
+size_t sweep_cluster_smem_bytes(int nlevels, int logc);
+cudaError_t launch_sweep_cluster(const SweepParams& p, int logc, int block, cudaStream_t stream, int* launches, int* levels);
 int sweep_grid_groups(const SweepParams& p, int max_groups, int* total_ctas_out, int* group_ctas_out);
 cudaError_t launch_sweep_grid(const SweepParams& p, int ngroups, unsigned* counters, cudaStream_t stream,
                               int* launches, int* levels);

@@ -52,6 +52,7 @@ SIGNATURES = {
     "asora_set_sphere_only": (_i, [_i]),
     "asora_set_deterministic": (_i, [_i]),
     "asora_set_octant_shape": (_i, [_i, _i, _i, _i]),
+    "asora_set_cluster_shape": (_i, [_i, _i]),
     "asora_plan_builds": (_i, []),
     "asora_plan_export": (_i64, [_i, _d, _d, _i, _i, _i, _i64, c_dp, c_dp, ctypes.POINTER(ctypes.c_uint16),
                                  ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_uint8),
