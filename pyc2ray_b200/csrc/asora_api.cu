@@ -511,10 +511,15 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     // Large radii: one cluster per wedge with the level buffers in distributed shared memory (variant 4) while a CTA's
     // share of two levels fits its shared memory (up to ~1000^3 meshes with clusters of 8), else the grid-cooperative
     // sweep through L2 scratch grids (variant 2).
-    int clu_logc = 3, clu_block = 256;
+    int clu_logc = 3, clu_block = 384;
     if (variant == 4) {
         p.sphere_only = sphere_only ? 1 : 0;
         const int nl = sweep_cluster_levels(p);
+        // Cluster shape (measured, full 256^3 box): few sources want every SM on each of them -- 8 CTAs x 384 threads per
+        // wedge, 192 CTAs per source: 0.50 ms for one source (0.54 / 0.74 ms with 8 x 256 / 4 x 256); from a handful of
+        // sources on, 4 x 256 keeps three CTAs per SM busy: 59 G updates/s against 54 (8 x 256) and 47 (8 x 384).
+        if (count >= 4) { clu_logc = 2; clu_block = 256; }
+        if (sweep_cluster_smem_bytes(nl, clu_logc) > budget) { clu_logc = 3; clu_block = 256; }
         if (g.clu_logc > 0) clu_logc = g.clu_logc - 1;
         if (g.clu_block > 0) clu_block = g.clu_block;
         if (sweep_cluster_smem_bytes(nl, clu_logc) > budget) {

@@ -122,13 +122,15 @@ sweep_wedge_kernel(SweepParams p, int nlevels, int pitch, int rows_cap)
     for (int m = 0; m < nlevels; m++) {
         const int dom = sgn_dom * m;
         const bool level_in_box = dom >= p.last_l && dom <= p.last_r;
-        const int ncols = m + 1;
-        // my rows of this level: blocks g = rank, rank + C, ... of four rows, up to the block that holds row m
-        const int G = m >> 2;
+        // minor offsets of this level: 0 .. amax (the level's square clipped by the octahedron and by the cube)
+        const int amax = min(m, min(p.q_max - m, max(-p.last_l, p.last_r)));
+        const int ncols = amax + 1;
+        // my rows of this level: blocks g = rank, rank + C, ... of four rows, up to the block that holds row amax
+        const int G = amax >> 2;
         int nloc = 0;
-        if (level_in_box && G >= (int)rank) {
+        if (level_in_box && amax >= 0 && G >= (int)rank) {
             const int nblk = (G - (int)rank) / C + 1;
-            nloc = 4 * nblk - ((((G - (int)rank) % C) == 0) ? 3 - (m & 3) : 0);
+            nloc = 4 * nblk - ((((G - (int)rank) % C) == 0) ? 3 - (amax & 3) : 0);
         }
         const int total = nloc * ncols;
         double* cur = buf + (size_t)(m & 1) * rows_cap * pitch;
@@ -144,7 +146,7 @@ sweep_wedge_kernel(SweepParams p, int nlevels, int pitch, int rows_cap)
             // octahedron & cube (raytracing.cu:101,122-123,241)
             if (m + a + b > p.q_max || da < p.last_l || da > p.last_r || db < p.last_l || db > p.last_r) continue;
             const int n = m * m + a * a + b * b;
-            const double dn = (double)n;
+            const double dn = u2d((unsigned)n);  // (int -> fp64 on the fp64 pipe instead of the conversion unit)
             unsigned flags = 0;
             bool inside;
             if (dn <= R2_lo) {
@@ -168,13 +170,13 @@ sweep_wedge_kernel(SweepParams p, int nlevels, int pitch, int rows_cap)
             if ((m == 0 && sgn_dom < 0) || (a == 0 && sgnA < 0) || (b == 0 && sgnB < 0)) owner = false;
             if (m == 0) flags = PC_SOURCE | (owner ? PC_RATED : 0u);
             else if (inside && owner) flags = PC_RATED;
-            const size_t pos = (size_t)pos_dom + wrapA[da] + wrapB[db];
+            const unsigned pos = pos_dom + wrapA[da] + wrapB[db];  // N <= 1600: fits 32 bits
             const double ntau = __ldg(p.nhi + pos);
             double cin = 0.0, path = 0.5, inv_np = ASORA_FOURPI;
             if (m > 0) {
                 // fractions a/m, b/m correctly rounded (reciprocal + one correction step); path = sqrt(n)/m
                 // (raytracing.cu:444); 1/(n path) by reciprocal
-                const double ad = (double)a, bd = (double)b;
+                const double ad = u2d((unsigned)a), bd = u2d((unsigned)b);
                 const double qa = ad * inv_m, qb = bd * inv_m;
                 const double wA = fma(fma(-md, qa, ad), inv_m, qa), wB = fma(fma(-md, qb, bd), inv_m, qb);
                 const double sn = wedge_sqrt(dn), qp = sn * inv_m;
@@ -182,13 +184,14 @@ sweep_wedge_kernel(SweepParams p, int nlevels, int pitch, int rows_cap)
                 inv_np = fast_rcp(dn * path);
                 if (m == 1 && (a == 1 || b == 1)) flags |= (a == 1 && b == 1) ? PC_DIAG3 : PC_DIAG2;
                 // upstream rows a-1 and a, columns b-1 and b of the previous level; indices of zero-weight corners are
-                // clamped into the array (their values are masked in interp_coldens)
+                // clamped into the array: whatever finite value sits there is multiplied by an exact 0 (the buffers
+                // start zeroed and only ever receive optical depths)
                 const int am = max(a - 1, 0), au = min(a, m - 1), bm = max(b - 1, 0), bu = min(b, m - 1);
                 const unsigned row_m = map_to_rank(prev_addr + (unsigned)(row_local<LOGC>(am) * pitch * 8), row_owner<LOGC>(am));
                 const unsigned row_u = map_to_rank(prev_addr + (unsigned)(row_local<LOGC>(au) * pitch * 8), row_owner<LOGC>(au));
                 const double c1 = load_cluster(row_m + bm * 8), c2 = load_cluster(row_u + bm * 8);
                 const double c3 = load_cluster(row_m + bu * 8), c4 = load_cluster(row_u + bu * 8);
-                cin = interp_coldens<true, true>(c1, c2, c3, c4, wA, wB, flags);
+                cin = interp_coldens<false, true>(c1, c2, c3, c4, wA, wB, flags);
             }
             const double cdho = finish_cell<1, false, HEAT, DET>(cin, path, inv_np, flags, ntau, sk, pos, p, log2_tab);
             cur[lr * pitch + b] = cdho;

@@ -107,8 +107,10 @@ __device__ __forceinline__ void photo_lookup2(bool thick, double tau_in, double 
 {
     int h1 = __double2hiint(tau_in), h2 = __double2hiint(tau_out);
     if (__builtin_expect(((unsigned)(h1 - p.hi_min) >= p.hi_span) | ((unsigned)(h2 - p.hi_min) >= p.hi_span), 0)) {
-        tau_in = clamp_tau_slow(tau_in, p.tau_lo, p.tau_hi);
-        tau_out = clamp_tau_slow(tau_out, p.tau_lo, p.tau_hi);
+        // (selects, not a call: optically thick boxes reach the end of the table within tens of cells, so this path is
+        // not rare on large-radius sweeps -- profiles/r02c)
+        tau_in = dmin(dmax(tau_in, p.tau_lo), p.tau_hi);
+        tau_out = dmin(dmax(tau_out, p.tau_lo), p.tau_hi);
         h1 = __double2hiint(tau_in);
         h2 = __double2hiint(tau_out);
     }
@@ -238,6 +240,10 @@ __device__ __forceinline__ double finish_cell_pre(double tau_in, double path_cel
     if ((flags & PC_RATED) && tau_in <= p.tau_max) {  // coldensh_in <= MAX_COLDENSH (raytracing.cu:315)
         const double dtau = tau_out - tau_in;
         const bool thick = fabs(dtau) > ASORA_TAU_PHOTO_LIMIT;
+        // Beyond the end of the table both lookups of a thick cell are clamped to the same entry (rates.cu:78-79), so the
+        // reference adds exactly T - T = 0 there: nothing to look up or deposit.  In an optically thick box that is most
+        // of a large-radius sweep (tau reaches 10^4 within 44 cells of a source in the reference's benchmark field).
+        if (thick && tau_in >= p.tau_hi) return tau_out;
         double t_in, t_out, h_in = 0.0, h_out = 0.0;
         photo_lookup2<REP, TEX, HEAT>(thick, tau_in, tau_out, p, log2_tab, t_in, t_out, h_in, h_out);
         // rates.cu:28-38: thick cells absorb T(tau_in) - T(tau_out), thin cells dtau * T_thin(tau_out)

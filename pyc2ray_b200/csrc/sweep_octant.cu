@@ -195,6 +195,10 @@ __device__ __forceinline__ void entry_images(const int4 ra, const int4 rb, doubl
 #pragma unroll
             for (int u = 0; u < NB; u++)
                 if (!(((zmask & (unsigned)(gbase + tt[u])) == 0) && (tin[u] <= p.tau_max))) pos[u] = ASORA_NO_DEPOSIT;
+            // a thick cell wholly beyond the end of the table adds exactly T - T = 0 (both lookups clamp to the same entry)
+#pragma unroll
+            for (int u = 0; u < NB; u++)
+                if (tin[u] >= p.tau_hi && fabs(tout[u] - tin[u]) > ASORA_TAU_PHOTO_LIMIT) pos[u] = ASORA_NO_DEPOSIT;
             double sk_n[NB];
 #pragma unroll
             for (int u = 0; u < NB; u++) sk_n[u] = skn;

@@ -26,6 +26,8 @@ check(L.asora_set_sweep_variant(variant))
 if os.environ.get("ASORA_OCT_SHAPE"):  # "noct,opt,batch,block[,knobs]"
     f = [int(x) for x in os.environ["ASORA_OCT_SHAPE"].split(",")]
     check(L.asora_set_octant_shape(f[0], f[1], f[2], f[3] | ((f[4] if len(f) > 4 else 0) << 16)))
+if os.environ.get("ASORA_CLUSTER_SHAPE"):  # "ctas,threads"
+    check(L.asora_set_cluster_shape(*[int(x) for x in os.environ["ASORA_CLUSTER_SHAPE"].split(",")]))
 for r in range(reps):
     check(L.asora_raytrace_device(R, SIG, 3 * MPC / N, 0, ns, -20.0, dlogtau, 20000, 1)); check(L.asora_sync())
     ms, kms = ctypes.c_float(0), ctypes.c_float(0)
