@@ -7,5 +7,6 @@ from .chemistry import hydrogenODE
 from .radiation import make_tau_table, BlackBodySource, blackbody_tables
 from .utils.sourceutils import format_sources, generate_test_sources, read_test_sources
 from .c2ray_base import C2Ray, C2Ray_Test
+from .c2ray_244paper import C2Ray_244Test
 from .utils.logutils import printlog
 from . import evolve, raytracing, chemistry, asora_core, radiation, utils

@@ -64,7 +64,7 @@ def source_data_to_device(pos, flux, NumSrc):
     check(L.asora_source_data_to_device(iptr(pos), dptr(flux), int(NumSrc)))
 
 
-def do_all_sources(R, coldensh_out, sig, dr, ndens, xh_av, phi_ion, NumSrc, m1, minlogtau, dlogtau, NumTau, group=None,
+def do_all_sources(R, coldensh_out, sig, dr, ndens, xh_av, phi_ion, NumSrc, m1, minlogtau, dlogtau, NumTau, *, group=None,
                    download=True):
     """python_module.cu:21-68.  ``coldensh_out`` and ``ndens`` are accepted and ignored exactly as the
     reference ignores them (raytracing.cu:116); ``phi_ion`` is overwritten in place.
