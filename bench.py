@@ -264,6 +264,7 @@ class ReferenceKernel:
         L.ref_source_data_to_device.argtypes = [ip, dp, ctypes.c_int]
         L.ref_do_all_sources.argtypes = [ctypes.c_double, dp, ctypes.c_double, ctypes.c_double, dp, dp, dp, ctypes.c_int,
                                          ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int]
+        L.ref_zero_coldens.argtypes = [ctypes.c_int, ctypes.c_int]
         self.L = L
 
     @staticmethod
@@ -273,6 +274,7 @@ class ReferenceKernel:
     def setup(self, N, batch, ndens, thin, thick, pos_flat, flux_flat, ns):
         with quiet_stdout():
             assert self.L.ref_device_init(N, batch) == 0
+            assert self.L.ref_zero_coldens(N, batch) == 0  # the reference reads its scratch uninitialised (oracle/ref_shim.cu)
             self.L.ref_density_to_device(ndens.ctypes.data_as(self.dp), N)
             self.L.ref_photo_table_to_device(thin.ctypes.data_as(self.dp), thick.ctypes.data_as(self.dp), thin.size)
             self.L.ref_source_data_to_device(pos_flat.ctypes.data_as(self.ip), flux_flat.ctypes.data_as(self.dp), ns)

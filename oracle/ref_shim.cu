@@ -45,6 +45,14 @@ int ref_do_all_sources(double R, double* coldensh_out, double sig, double dr, do
     }
     return (int)cudaGetLastError();
 }
+// Zero the reference's column-density scratch (NUM_SRC_PAR x N^3 doubles).  The reference never initialises it and
+// multiplies whatever it reads for zero-weight corners by 0 (raytracing.cu:278-282,416-428): NaN bit patterns left in
+// freed device memory by an earlier user of the GPU then poison those cells (SURVEY note N3).  The harness gives the
+// reference a clean scratch; the reference code is untouched.
+int ref_zero_coldens(int N, int num_src_par)
+{
+    return (int)cudaMemset(cdh_dev, 0, sizeof(double) * (size_t)N * N * N * (size_t)num_src_par);
+}
 // device -> host copy of batch slot 0 of the reference's column-density scratch (memory.cu:20)
 int ref_copy_coldens(double* host, int N)
 {

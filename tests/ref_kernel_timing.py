@@ -35,6 +35,7 @@ for R in (10.0, 30.0):
     sphere = 4.0 / 3.0 * np.pi * R ** 3
     for batch in (32, 64, 96, 128):
         assert R_.ref_device_init(N, batch) == 0
+        R_.ref_zero_coldens(N, batch)
         R_.ref_density_to_device(ndens.ctypes.data_as(dp), N)
         R_.ref_photo_table_to_device(thin.ctypes.data_as(dp), thick.ctypes.data_as(dp), 20000)
         R_.ref_source_data_to_device(pos_flat.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), flux_flat.ctypes.data_as(dp), ns)

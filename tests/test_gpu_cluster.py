@@ -104,6 +104,7 @@ def test_cluster_full_box_128_vs_reference_kernel():
         L.ref_do_all_sources.argtypes = [ctypes.c_double, dp, ctypes.c_double, ctypes.c_double, dp, dp, dp, ctypes.c_int,
                                          ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int]
         L.ref_copy_coldens.argtypes = [dp, ctypes.c_int]
+        L.ref_zero_coldens.argtypes = [ctypes.c_int, ctypes.c_int]
         ref_phi, _ = run_reference(L, c, batch=6)
         _assert_close(phi, ref_phi, "cluster sweep vs the reference kernel, full 128^3 box")
 

@@ -25,6 +25,7 @@ def ref():
     L.ref_do_all_sources.argtypes = [ctypes.c_double, dp, ctypes.c_double, ctypes.c_double, dp, dp, dp, ctypes.c_int,
                                      ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int]
     L.ref_copy_coldens.argtypes = [dp, ctypes.c_int]
+    L.ref_zero_coldens.argtypes = [ctypes.c_int, ctypes.c_int]
     return L
 
 
@@ -38,6 +39,7 @@ def run_reference(L, c, batch=4, want_cdh=False):
     phi = np.zeros(N ** 3)
     dummy = np.zeros(N ** 3)
     assert L.ref_device_init(N, batch) == 0
+    assert L.ref_zero_coldens(N, batch) == 0   # the reference reads its scratch uninitialised (oracle/ref_shim.cu)
     L.ref_density_to_device(nd.ctypes.data_as(dp), N)
     L.ref_photo_table_to_device(thin.ctypes.data_as(dp), thick.ctypes.data_as(dp), thin.size)
     L.ref_source_data_to_device(pos.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), flux.ctypes.data_as(dp), flux.size)
