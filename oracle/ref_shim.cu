@@ -22,13 +22,24 @@ int ref_device_init(int N, int num_src_par)
     }
     return 0;
 }
-void ref_device_close(void) { device_close(); }
+// device_close frees the source arrays (memory.cu:119-129) but leaves the pointers set, and the next
+// source_data_to_device frees them AGAIN (memory.cu:102-103).  In one process that second cudaFree hits whatever was
+// allocated at that address in between -- typically the reference's own freshly uploaded photo tables (same size class),
+// which the new source arrays then overwrite: the first table entries become source coordinates and the source cells get
+// garbage rates.  A driver script never sees this (one device_init per process); a test harness that cycles
+// device_init / device_close does.  The harness clears the dangling pointers (cudaFree(nullptr) is a no-op); the
+// reference code is untouched.
+void ref_device_close(void)
+{
+    device_close();
+    src_pos_dev = nullptr;
+    src_flux_dev = nullptr;
+    photo_thin_table_dev = nullptr;
+}
 void ref_density_to_device(double* ndens, int N) { density_to_device(ndens, N); }
 void ref_photo_table_to_device(double* thin, double* thick, int NumTau) { photo_table_to_device(thin, thick, NumTau); }
-// source_data_to_device frees the previous pointers first (memory.cu:102-103); after a
-// device_close()/device_init() cycle in one process those are dangling, cudaFree fails with
-// cudaErrorInvalidValue, and the reference later reports that stale error as a launch failure
-// (raytracing.cu:134).  The harness drops the stale error; the reference code is untouched.
+// source_data_to_device frees the previous pointers first (memory.cu:102-103); should that fail, the reference later
+// reports the stale error as a launch failure (raytracing.cu:134).  The harness drops it; the reference code is untouched.
 void ref_source_data_to_device(int* pos, double* flux, int NumSrc)
 {
     source_data_to_device(pos, flux, NumSrc);
