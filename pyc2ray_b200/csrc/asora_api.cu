@@ -401,10 +401,11 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     const int hi_cells = std::min(p.q_max, std::max(-p.last_l, p.last_r));
     const bool symmetric = std::min(p.q_max, p.last_r) == std::min(p.q_max, -p.last_l) && hi_cells <= 126;
     const size_t budget = (size_t)g.smem_optin;
-    // automatic choice (measured, scripts/octant_probe.py): the mirror-image sweep wins on full-octahedron sweeps of large
-    // radii (R = 30: 16.3 vs 17.0 ms); sphere-only sweeps and small radii stay on variant 1 (R = 30 sphere-only: 11.2 vs
-    // 11.9 ms; R = 10.76: 8.4 vs 11.3 ms)
-    const bool auto_octant = !sphere_only && hi_cells >= 32 && !g.heating;
+    // automatic choice (measured, scripts/octant_probe.py, profiles/r02f_radius_sweep_256.md): the mirror-image sweep wins on
+    // full-octahedron sweeps whose eight octants just fit one SM (R = 30: 16.3 vs 17.0 ms for 10^4 sources); smaller
+    // radii, larger radii (split sweeps) and sphere-only sweeps stay on variant 1 (R = 20: 5.7 vs 7.2 ms; R = 40: 10.7 vs
+    // 11.6 ms; R = 30 sphere-only: 11.2 vs 11.9 ms; R = 10.76: 8.4 vs 11.3 ms)
+    const bool auto_octant = !sphere_only && hi_cells >= 44 && hi_cells <= 60 && !g.heating;
     if ((variant == 3 || (variant == 0 && auto_octant)) && symmetric && !coldens_grid) {
         std::string err;
         plan = get_plan(N, R, dr, sphere_only, true, 1, err);
@@ -417,6 +418,7 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
                 if (variant == 3) return fail("sweep variant 3 forced but a level does not fit in shared memory");
                 plan = nullptr;
             }
+            if (plan && variant == 0 && noct < 8) plan = nullptr;  // automatic: only while all eight octants fit one CTA
         }
         if (plan) {
             // Launch shape (measured on B200, scripts/octant_probe.py; DESIGN.md, "Mirror-image sweep").  Large levels:
