@@ -623,7 +623,7 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
         if (e != cudaSuccess) return fail_cuda("sweep_wedge_kernel launch", e);
     } else if (variant == 3) {
         g.last_levels = plan->nlevels;
-        if (p.zface_offset && sweep_octant_smem_bytes(*plan, noct, (opts & 1) ? 8 : 1, true) > budget) opts &= ~1;
+        if (p.zface_offset && sweep_octant_smem_bytes(*plan, noct, (opts & 1) ? 8 : 1, true) > budget && noct == 8) opts &= ~1;
         cudaError_t e = launch_sweep_octant(*plan, p, noct, opt, batch, block, opts, g.stream, &g.last_launches);
         if (e != cudaSuccess) return fail_cuda("sweep_octant_kernel launch", e);
     } else {

@@ -39,6 +39,19 @@ namespace {
 
 #define ASORA_NO_DEPOSIT 0xffffffffu
 
+// Plan entries are streamed: every CTA reads each entry of a level once.  Loading them without allocating in L1 leaves
+// the L1 to the opacity gathers, which neighbouring sources on the same SM do share.
+__device__ __forceinline__ int4 load_plan(const int4* __restrict__ ptr)
+{
+#ifdef ASORA_PLAN_L1_ALLOCATE
+    return __ldg(ptr);
+#else
+    int4 v;
+    asm("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+    return v;
+#endif
+}
+
 // Phase 2 for NB cells side by side: rates.cu:16-41 + the deposit of raytracing.cu:324-329 (finish_cell_pre in
 // sweep_device.cuh is the one-cell form).  pos[u] == ASORA_NO_DEPOSIT: nothing to deposit for that cell.
 template <int NB, int REP, bool TEX, bool HEAT, bool DET>
@@ -225,8 +238,8 @@ __device__ __forceinline__ void octant_level(const int4* __restrict__ plan, int 
     int e = beg + (warp / G) * 32 + lane;
     int4 ra_next = make_int4(0, 0, 0, 0), rb_next = make_int4(0, 0, 0, 0);
     if (PF && e < end) {  // PF: the entry of the next iteration is fetched while this one is evaluated
-        rb_next = __ldg(plan + (size_t)ncells + e);
-        ra_next = __ldg(plan + e);
+        rb_next = load_plan(plan + (size_t)ncells + e);
+        ra_next = load_plan(plan + e);
     }
     for (; e < end; e += BLOCK / G) {
         int4 ra, rb;
@@ -235,12 +248,12 @@ __device__ __forceinline__ void octant_level(const int4* __restrict__ plan, int 
             rb = rb_next;
             const int en = e + BLOCK / G;
             if (en < end) {
-                rb_next = __ldg(plan + (size_t)ncells + en);
-                ra_next = __ldg(plan + en);
+                rb_next = load_plan(plan + (size_t)ncells + en);
+                ra_next = load_plan(plan + en);
             }
         } else {
-            rb = __ldg(plan + (size_t)ncells + e);
-            ra = __ldg(plan + e);
+            rb = load_plan(plan + (size_t)ncells + e);
+            ra = load_plan(plan + e);
         }
         const int di = rb.z & 0xff, dj = (rb.z >> 8) & 0xff, dk = (rb.z >> 16) & 0xff;
         // PC_ZFACE: second set of wrap tables, addressing the (k,i,j)-ordered copies of the opacity and rate grids
@@ -367,9 +380,11 @@ cudaError_t launch_opts(const SweepPlan& plan, const SweepParams& p, int opts, c
     }
     if (p.zface_offset) {
         if constexpr (BIG) {
-            if ((opts & 5) == 5) return launch_t<BLOCK, MINB, NOCT, OPT, BATCH, 8, true, false, true, true>(plan, p, dedup, stream);
+            // copies of the log2 table: eight for one CTA per SM, four where two or more CTAs share an SM's shared memory
+            constexpr int REPX = MINB >= 2 ? 4 : 8;
+            if ((opts & 5) == 5) return launch_t<BLOCK, MINB, NOCT, OPT, BATCH, REPX, true, false, true, true>(plan, p, dedup, stream);
             if (opts & 4) return launch_t<BLOCK, MINB, NOCT, OPT, BATCH, 1, true, false, true, true>(plan, p, dedup, stream);
-            if (opts & 1) return launch_t<BLOCK, MINB, NOCT, OPT, BATCH, 8, true, false, true, false>(plan, p, dedup, stream);
+            if (opts & 1) return launch_t<BLOCK, MINB, NOCT, OPT, BATCH, REPX, true, false, true, false>(plan, p, dedup, stream);
             return launch_t<BLOCK, MINB, NOCT, OPT, BATCH, 1, true, false, true, false>(plan, p, dedup, stream);
         } else {
             return cudaErrorInvalidValue;
