@@ -64,7 +64,8 @@ int asora_do_all_sources(double R, double sig, double dr, const double* xh_av, d
 
 /* The two halves of asora_do_all_sources, for callers that put a collective between the sweep and the download (one
  * process per GPU, sources sharded over the ranks, pyc2ray/evolve.py:360-373,433-437): _begin copies xh_av to the
- * device and queues the sweep of the first NumSrc uploaded sources on the context's stream; the caller then reduces
+ * device (or, with xh_av == NULL, takes what ASORA_BUF_XH_AV already holds: a rank that received the grid from a peer
+ * GPU instead of from its host) and queues the sweep of the first NumSrc uploaded sources on the context's stream; the caller then reduces
  * ASORA_BUF_PHI_ION over the ranks on that stream (asora_set_stream, asora_device_buffer); _end waits and copies the
  * rates to phi_ion, or only waits when phi_ion is NULL (a rank that does not need the grid on the host). */
 int asora_do_all_sources_begin(double R, double sig, double dr, const double* xh_av, int NumSrc, int N,

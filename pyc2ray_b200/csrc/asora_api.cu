@@ -982,8 +982,9 @@ int asora_do_all_sources_begin(double R, double sig, double dr, const double* xh
 {
     if (int rc = need_init()) return rc;
     if (N != g.N) return fail("do_all_sources_begin: m1 differs from device_init");
-    if (!xh_av) return fail("do_all_sources_begin: null pointer");
-    if (int rc = host_copy(g.buf[ASORA_BUF_XH_AV], xh_av, sizeof(double) * g.ncell, cudaMemcpyHostToDevice)) return rc;
+    // xh_av == NULL: ASORA_BUF_XH_AV already holds the fractions (a rank that received them from a peer over NVLink)
+    if (xh_av)
+        if (int rc = host_copy(g.buf[ASORA_BUF_XH_AV], xh_av, sizeof(double) * g.ncell, cudaMemcpyHostToDevice)) return rc;
     return run_sweep(R, sig, dr, 0, NumSrc, minlogtau, dlogtau, NumTau, true, nullptr);
 }
 

@@ -44,7 +44,7 @@ def _upload(buf, a):
 
 def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table, minlogtau, dlogtau, R_max_LLS,
                    convergence_fraction, sig, bh00, albpow, colh0, temph0, abu_c, logfile, quiet, shard=None,
-                   group=None, max_iter=10000, decomposition="list"):
+                   group=None, max_iter=10000, decomposition="list", io_rank=None):
     if not cuda_is_init():
         raise RuntimeError("GPU not initialized. Please initialize it by calling device_init(N)")
     NumSrc_total = src_flux.shape[0]
@@ -83,7 +83,19 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
         raise ValueError("rsag decomposition needs N^3 divisible by the number of ranks")
 
     check(L.asora_source_data_to_device(iptr(srcpos_flat), dptr(normflux_flat), NumSrc))
-    if halo is None or _is_f(ndens) or _is_f(temp) or _is_f(xh):
+    if nprocs > 1 and io_rank is not None:
+        # one rank reads the grids from its host; the others receive them from that GPU over NVLink (three broadcasts of
+        # 8 N^3 bytes) instead of nprocs uploads through the host's memory system
+        import torch
+        import torch.distributed as dist
+        for buf, arr in ((_cabi.BUF_NDENS, ndens), (_cabi.BUF_TEMP, temp), (_cabi.BUF_XH, xh)):
+            if rank == io_rank:
+                _upload(buf, arr)
+            t = device_tensor(L.asora_device_buffer(buf), NumCells)
+            dist.broadcast(t, src=dist.get_global_rank(group, io_rank) if group is not None else io_rank, group=group)
+        torch.cuda.synchronize()
+        check(L.asora_invalidate_temperature())
+    elif halo is None or _is_f(ndens) or _is_f(temp) or _is_f(xh):
         _upload(_cabi.BUF_NDENS, ndens)
         _upload(_cabi.BUF_TEMP, temp)
         _upload(_cabi.BUF_XH, xh)
@@ -204,6 +216,9 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
         torch.cuda.synchronize()
     if rank == 0:
         printlog("Multiple source convergence reached.", logfile, quiet)
+    evolve3D.last_niter = niter
+    if nprocs > 1 and io_rank is not None and rank != io_rank:
+        return None, None  # only io_rank wanted the grids on its host
     phi_ion = np.empty(NumCells)
     check(L.asora_buffer_download(_cabi.BUF_PHI_ION, dptr(phi_ion)))
     if _is_f(xh):
@@ -239,7 +254,7 @@ evolve3D.last_niter = 0
 
 def evolve3D_dist(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table, photo_thick_table, minlogtau,
                   dlogtau, R_max_LLS, convergence_fraction, sig, bh00, albpow, colh0, temph0, abu_c,
-                  logfile="pyC2Ray.log", quiet=False, group=None, decomposition="auto"):
+                  logfile="pyC2Ray.log", quiet=False, group=None, decomposition="auto", io_rank=None):
     """Source-sharded time step over the ranks of an initialised torch.distributed process group
     (backend nccl, one rank per GPU).  Every rank passes the full source list and gets the full
     result.
@@ -249,13 +264,17 @@ def evolve3D_dist(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table, 
     chemistry and broadcasts); "rsag" -- the same sharding with a reduce-scatter of phi_ion, chemistry on the rank's
     N^3/nprocs cells and an all-gather of xh_av; "slab" -- sources sharded by position, halo exchanges
     instead of N^3 collectives (parallel.SlabHalo); "auto" -- slab when the slabs are wide enough for the ray-tracing
-    radius, else rsag when N^3 divides by the number of ranks, else list."""
+    radius, else rsag when N^3 divides by the number of ranks, else list.
+
+    io_rank: None -- every rank passes the full grids and gets the full result (the reference's semantics); r -- only rank
+    r's ``temp``, ``ndens``, ``xh`` are read (the other ranks receive them GPU to GPU over NVLink) and only rank r gets the
+    result (the others return ``(None, None)``): one set of host<->device copies per time step instead of one per rank."""
     import torch.distributed as dist
     rank, nprocs = dist.get_rank(group), dist.get_world_size(group)
     shard = (rank, nprocs) if src_flux.shape[0] >= nprocs else None  # c2ray_base.py:185
     return _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table, minlogtau, dlogtau,
                           R_max_LLS, convergence_fraction, sig, bh00, albpow, colh0, temph0, abu_c, logfile,
-                          quiet or rank != 0, shard=shard, group=group, decomposition=decomposition)
+                          quiet or rank != 0, shard=shard, group=group, decomposition=decomposition, io_rank=io_rank)
 
 
 def evolve3D_MPI(dt, dr, src_flux, src_pos, use_gpu, max_subbox, subboxsize, loss_fraction, use_mpi, comm, rank,

@@ -65,7 +65,7 @@ def source_data_to_device(pos, flux, NumSrc):
 
 
 def do_all_sources(R, coldensh_out, sig, dr, ndens, xh_av, phi_ion, NumSrc, m1, minlogtau, dlogtau, NumTau, *, group=None,
-                   download=True):
+                   download=True, xh_from=None):
     """python_module.cu:21-68.  ``coldensh_out`` and ``ndens`` are accepted and ignored exactly as the
     reference ignores them (raytracing.cu:116); ``phi_ion`` is overwritten in place.
 
@@ -73,11 +73,15 @@ def do_all_sources(R, coldensh_out, sig, dr, ndens, xh_av, phi_ion, NumSrc, m1, 
     ranks each hold a shard of the sources on their own GPU.  The rates of all ranks are then summed on the devices by
     one NCCL all-reduce between the sweep and the download -- the reference's Reduce + Bcast of host arrays
     (pyc2ray/evolve.py:433-437) -- and ``download=False`` lets a rank skip the device-to-host copy when it does not
-    need the grid on the host."""
+    need the grid on the host.  ``xh_from=r``: the ionised fractions are the same on every rank (they are in a
+    source-sharded run), so only rank ``r`` copies its ``xh_av`` to its GPU and the others receive it from that GPU over
+    NVLink (one NCCL broadcast of 8 N^3 bytes) instead of N uploads through the host's memory system; the ``xh_av``
+    argument of the other ranks is not read."""
     if not isinstance(coldensh_out, np.ndarray) or coldensh_out.dtype != np.float64:
         raise TypeError("coldensh_out must be Array of type double")  # python_module.cu:53-57
     n3 = int(m1) ** 3
-    _f64(xh_av, "xh_av", n3)
+    if group is None or xh_from is None:
+        _f64(xh_av, "xh_av", n3)
     _f64(phi_ion, "phi_ion", n3)
     if not phi_ion.flags.writeable:
         raise ValueError("phi_ion must be writeable")
@@ -88,11 +92,20 @@ def do_all_sources(R, coldensh_out, sig, dr, ndens, xh_av, phi_ion, NumSrc, m1, 
     import torch
     import torch.distributed as dist
     from ..parallel import device_tensor
-    check(L.asora_do_all_sources_begin(float(R), float(sig), float(dr), dptr(xh_av), int(NumSrc), int(m1), float(minlogtau),
+    grp = None if group is True else group
+    if xh_from is None:
+        xh_ptr = dptr(xh_av)
+    else:
+        if dist.get_rank(grp) == xh_from:
+            check(L.asora_buffer_upload(_cabi.BUF_XH_AV, dptr(_f64(xh_av, "xh_av", n3))))
+        xav_t = device_tensor(L.asora_device_buffer(_cabi.BUF_XH_AV), n3)
+        dist.broadcast(xav_t, src=dist.get_global_rank(grp, xh_from) if grp is not None else xh_from, group=grp)
+        xh_ptr = None
+    check(L.asora_do_all_sources_begin(float(R), float(sig), float(dr), xh_ptr, int(NumSrc), int(m1), float(minlogtau),
                                        float(dlogtau), int(NumTau)))
     phi_t = device_tensor(L.asora_device_buffer(_cabi.BUF_PHI_ION), n3)
     torch.cuda.nvtx.range_push("asora:allreduce_phi")
-    dist.all_reduce(phi_t, op=dist.ReduceOp.SUM, group=None if group is True else group)
+    dist.all_reduce(phi_t, op=dist.ReduceOp.SUM, group=grp)
     torch.cuda.synchronize()
     torch.cuda.nvtx.range_pop()
     check(L.asora_do_all_sources_end(dptr(phi_ion) if download else None))

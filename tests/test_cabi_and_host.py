@@ -98,7 +98,7 @@ def test_boundary_signatures_match_reference():
     # the twelve positional parameters of the reference; the multi-GPU extras (group, download) are keyword-only
     pos = [n for n, q in inspect.signature(libasora.do_all_sources).parameters.items() if q.kind != q.KEYWORD_ONLY]
     assert pos == ["R", "coldensh_out", "sig", "dr", "ndens", "xh_av", "phi_ion", "NumSrc", "m1", "minlogtau", "dlogtau", "NumTau"]
-    assert sig(libasora.do_all_sources)[12:] == ["group", "download"]
+    assert sig(libasora.do_all_sources)[12:] == ["group", "download", "xh_from"]
     assert sig(libasora.device_init) == ["N", "num_src_par"]
     assert sig(libasora.density_to_device) == ["ndens", "N"]
     assert sig(libasora.photo_table_to_device) == ["thin_table", "thick_table", "NumTau"]
