@@ -533,6 +533,7 @@ def strong_512(p, thin, thick, dlogtau, rank, world, N=512, nsrc=100000):
                 x1, _ = p.evolve3D(*args, True, 1000, 64, 1e-2, *tail, logfile=None, quiet=True)
                 t1 = min(t1 or 1e30, time.perf_counter() - t0)
             out["iterations"] = p.evolve3D.last_niter
+            loop1 = p.evolve3D.last_loop_seconds
         dist.barrier()
         def timed(**kw):
             best, res = None, None
@@ -541,15 +542,20 @@ def strong_512(p, thin, thick, dlogtau, rank, world, N=512, nsrc=100000):
                 t0 = time.perf_counter()
                 res, _ = p.evolve3D_dist(*args, *tail, logfile=None, quiet=True, decomposition="auto", **kw)
                 torch.cuda.synchronize()
-                el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+                el = torch.tensor([time.perf_counter() - t0, p.evolve3D.last_loop_seconds], dtype=torch.float64, device="cuda")
                 dist.all_reduce(el, op=dist.ReduceOp.MAX)
-                best = min(best or 1e30, float(el))
+                if best is None or float(el[0]) < best[0]:
+                    best = (float(el[0]), float(el[1]))
             return best, res
-        tn, xd = timed(io_rank=0)     # one host copy of the grids in, one out (rank 0), GPU-to-GPU broadcast of the inputs
-        tn_all, _ = timed()           # the reference's semantics: every rank passes and receives all grids
+        (tn, loopn), xd = timed(io_rank=0)  # one host copy of the grids in, one out (rank 0), GPU-to-GPU broadcast of the inputs
+        (tn_all, _), _ = timed()            # the reference's semantics: every rank passes and receives all grids
         if rank == 0:
             out.update({"ms_1gpu": 1e3 * t1, "ms": 1e3 * tn, "speedup": t1 / tn, "efficiency_vs_1gpu": t1 / tn / world,
                         "ms_every_rank_copies": 1e3 * tn_all, "xh_max_rel_vs_1gpu": max_rel(xd, x1, 1e-300),
+                        "device_loop": {"ms_1gpu": 1e3 * loop1, "ms": 1e3 * loopn, "speedup": loop1 / loopn,
+                                        "efficiency_vs_1gpu": loop1 / loopn / world,
+                                        "what": "the convergence loop alone (sweeps, exchanges, chemistry, 3 scalars per iteration to the "
+                                                "host), grids resident on the devices"},
                         "what": "wall clock of the whole evolve3D(_dist) call incl. the host<->device copies of five 1.07 GB "
                                 "grids; ms: io_rank=0 (rank 0 reads and returns the grids, inputs broadcast over NVLink); "
                                 "ms_every_rank_copies: every rank uploads and downloads all five grids (reference semantics)",

@@ -134,6 +134,7 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
     flag = ctypes.c_int(0)
     s1 = ctypes.c_double(0.0)
     s0 = ctypes.c_double(0.0)
+    t_loop0 = time.perf_counter()
     try:
         # process-global sweep settings: switched on inside the try so that the finally below always resets them
         # The evolve loop only consumes phi_ion, so the sweep may skip the cells outside the R_max sphere
@@ -204,6 +205,7 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
     finally:
         L.asora_set_sphere_only(0)
         L.asora_set_active_slab(0, 0)
+    evolve3D.last_loop_seconds = time.perf_counter() - t_loop0  # the convergence loop alone: no host<->device grid copies
     if rsag:
         # once per time step: every rank gets the whole grids back (the reference API returns full arrays)
         allgather_chunks_(device_tensor(L.asora_device_buffer(_cabi.BUF_XH_INTERMED), NumCells), rank, nprocs, group)
@@ -250,6 +252,7 @@ def evolve3D(dt, dr, src_flux, src_pos, use_gpu, max_subbox, subboxsize, loss_fr
 
 
 evolve3D.last_niter = 0
+evolve3D.last_loop_seconds = 0.0
 
 
 def evolve3D_dist(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table, photo_thick_table, minlogtau,
