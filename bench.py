@@ -731,6 +731,46 @@ def main():
                 el = reduce_max(s0_.elapsed_time(s1_))
                 if rep > 0:
                     tn = min(tn or 1e30, el)
+            # the same problem sharded by position (parallel.slab_edges / SlabHalo, what evolve3D_dist's "auto" uses when the
+            # slabs are wide enough): a rank's rates stay within its planes +- a halo, so two halo exchanges with the
+            # neighbours replace the N^3 all-reduce; every rank ends with the complete rates of its OWN planes
+            slab = None
+            from pyc2ray_b200.parallel import slab_edges, SlabHalo
+            edges, hh = slab_edges(pos0[0::3], N, world, R)
+            if edges is not None:
+                halo = SlabHalo(edges, hh, N, rank, world)
+                o, cnt = halo.own_cells()
+                want = phi_t[o:o + cnt].clone()          # the all-reduced rates of the list-order run, my planes
+                mine = (pos0[0::3] >= halo.lo) & (pos0[0::3] < halo.hi)
+                nmine = int(mine.sum())
+                pos_m = np.ascontiguousarray(pos0.reshape(-1, 3)[mine].ravel())
+                libasora.source_data_to_device(pos_m, np.ascontiguousarray(flux0[mine]), nmine)
+                ts = None
+                for rep in range(4):
+                    barrier()
+                    s0_, s1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s0_.record(stream)
+                    check(L.asora_raytrace_device(R, SIG, dr, 0, nmine, -20.0, dlogtau, numtau, 1))
+                    halo.reduce_phi_(phi_t)
+                    s1_.record(stream)
+                    barrier()
+                    el = reduce_max(s0_.elapsed_time(s1_))
+                    if rep > 0:
+                        ts = min(ts or 1e30, el)
+                torch.cuda.synchronize()
+                got = phi_t[o:o + cnt]
+                scale = float(want.abs().max().item())
+                rel = ((got - want).abs() / torch.clamp(want.abs(), min=1e-12 * scale)).max().reshape(1)
+                dist.all_reduce(rel, op=dist.ReduceOp.MAX)
+                counts = torch.tensor([float(nmine)], device="cuda")
+                dist.all_reduce(counts, op=dist.ReduceOp.MAX)
+                slab = {"ms": ts, "halo_planes": hh, "max_sources_per_rank": int(counts.item()),
+                        "max_rel_vs_allreduce": float(rel.item()),
+                        "what": "sources sharded by x-plane ranges of equal source counts, sweep + two halo reductions of "
+                                f"{hh} planes ({hh * N * N * 8 / 1e6:.0f} MB each) with the neighbouring ranks; every rank ends with "
+                                "the complete rates of its own planes (the input of its share of the chemistry)"}
+                if slab["max_rel_vs_allreduce"] > 1e-10:
+                    failures.append("strong.fixed_256.slab")
             if rank == 0:
                 strong = {"fixed_256": {"sources_total": args.nsrc, "ms_1gpu": t1, "ms": tn, "speedup": t1 / tn,
                                         "efficiency_vs_1gpu": t1 / tn / world,
@@ -738,6 +778,10 @@ def main():
                                                 "sweep + all-reduce of phi_ion (134 MB), CUDA events, max over ranks",
                                         "limited_by": "the all-reduce and the fixed passes (opacity pre-pass, zeroing, division: "
                                                       "~0.3 ms) do not shrink with the shard"}}
+                if slab is not None:
+                    slab["speedup"] = t1 / slab["ms"]
+                    slab["efficiency_vs_1gpu"] = t1 / slab["ms"] / world
+                    strong["fixed_256"]["slab"] = slab
             libasora.source_data_to_device(pos_flat, flux_flat, args.nsrc)
 
         # ---- parity: the first 8 sources of rank 0's inputs, default launch shape, against the reference ----------

@@ -85,6 +85,7 @@ struct Context {
     int oct_noct = 0, oct_opt = 0, oct_batch = 0, oct_block = 0;  // forced shape of the mirror-image sweep (0 = automatic)
     int oct_opts = 0;                                              // its profiling knobs
     int clu_logc = 0, clu_block = 0;  // forced cluster size (log2) and threads of the large-radius sweep (0 = automatic)
+    int large_smem_min_sources = 4;   // q_max > 127: fewer sources than this go to the cluster sweep (R = 80, 4 sources: equal)
     int slab_begin = 0, slab_count = 0;  // active planes of a slab-decomposed run (0 = whole grid)
     int sphere_only = 0;
     int deterministic = 0;            // asora_set_deterministic: fixed-point accumulation of the rates
@@ -450,14 +451,27 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     }
     if (variant == 3 && !plan) return fail("sweep variant 3 forced but the swept region is not mirror-symmetric");
     if (variant != 2 && variant != 3) {
-        const int lo_side = 2 * hi_cells + 1;
-        if (p.q_max <= 127 && lo_side <= 255) {
+        const int side = std::min(p.q_max, p.last_r) + std::min(p.q_max, -p.last_l) + 1;
+        // Beyond q_max = 127 only the eight-octant split can fit, and only up to R ~ 100 cells at 256^3: counted before a
+        // plan of up to N^3 entries is built.  Few sources at such radii are better spread over every SM (variant 4).
+        // (measured, 256^3: R = 80, 128 sources 105 G updates/s against 30 with the wedge clusters, R = 100, 64 sources 86
+        // against 39; full 128^3 box, 256 sources 129 against 51: a plan entry replaces ~130 instructions of geometry)
+        bool large_ok = true;
+        if (p.q_max > 127 && side <= 256 && g.tune_parts == 0) {
+            large_ok = variant == 1 || count >= g.large_smem_min_sources;
+            if (large_ok) {
+                const size_t cells = (size_t)sweep_plan_octant_level_cells(N, R, dr, sphere_only);
+                large_ok = 256 * sizeof(double2) + 2 * cells * sizeof(double) + 6 * (size_t)side * sizeof(unsigned) +
+                           (size_t)(hi_cells + 2) * sizeof(int) <= budget;
+            }
+        }
+        if (side <= 256 && large_ok) {
             // Parts: start from the whole sweep and split (half-spaces, quadrants, octants) only until one
             // source's two level buffers fit in shared memory.  (Measured at R = 30, 256^3: 1 part x 1024
             // threads 20.6 ms, 2 x 512: 21.4, 4 x 256: 21.2, 8 x 256 with two sources: 21.1 -- splitting does
             // not pay by itself, it extends the shared-memory variant to radii of ~65 cells.)  The split found for a
             // (mesh, radius, cell size) is remembered, so that later sweeps go straight to the cached plan.
-            int parts = g.tune_parts > 0 ? g.tune_parts : 1;
+            int parts = g.tune_parts > 0 ? g.tune_parts : (p.q_max > 127 ? 8 : 1);
             Context::AutoParts* memo = nullptr;
             if (g.tune_parts == 0) {
                 for (auto& a : g.auto_parts)

@@ -135,6 +135,7 @@ __device__ __forceinline__ double fast_div(double a, double b)
 int asora_qmax(int N, double R);
 int64_t asora_count_cells(int N, double R);
 // upload = false: host-side plan only (plan.cells, level_start, level_mid), no device needed
+int sweep_plan_octant_level_cells(int N, double R, double dr, bool sphere_only);
 bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_only, int parts, std::string& err,
                       bool upload = true);
 int64_t asora_count_rated_cells(int N, double R, double dr);

@@ -117,6 +117,30 @@ static bool upload_plan(SweepPlan& plan, std::string& err)
     return true;
 }
 
+// Cells of the largest level of the largest octant (the all-negative one on even meshes) of an eight-part plan,
+// counted without building it: decides whether a large radius fits the shared-memory variant before a plan of
+// up to N^3 entries is made.
+int sweep_plan_octant_level_cells(int N, double R, double dr, bool sphere_only)
+{
+    const int Q = asora_qmax(N, R);
+    int ll, lr;
+    clip_bounds(N, ll, lr);
+    const int lo = std::max(ll, -Q);
+    const double R2 = R * R;
+    std::vector<int> count((size_t)(-lo) + 1, 0);
+    for (int i = lo; i <= 0; i++)
+        for (int j = lo; j <= 0; j++) {
+            const int kmin = std::max(lo, -(Q + i + j));  // |i| + |j| + |k| <= Q
+            for (int k = kmin; k <= 0; k++) {
+                if (sphere_only && !cell_rated(i, j, k, dr, R2)) continue;
+                count[(size_t)std::max(-i, std::max(-j, -k))]++;
+            }
+        }
+    int maxc = 0;
+    for (int c : count) maxc = std::max(maxc, c);
+    return maxc + 1;  // + the zero slot
+}
+
 // One sweep may be split into `parts` in {1,2,4,8} independent pieces by the signs of the offsets on z,
 // (y,z) or (x,y,z): every non-zero interpolation weight points one step towards the source, so a cell's
 // upstream cells have offsets of the same sign or zero, and a zero offset only ever pairs with the weight of
@@ -136,7 +160,7 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_o
     clip_bounds(N, ll, lr);
     const int lo = std::max(ll, -Q), hi = std::min(lr, Q);
     const int side = hi - lo + 1;
-    if (Q > 127 || side > 255) {
+    if (side > 256) {  // positions inside the swept cube are stored as bytes
         err = "sweep plan: radius too large for the shared-memory variant";
         return false;
     }
@@ -178,22 +202,28 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_o
 
     for (int part = 0; part < parts; part++) {
         std::fill(slot.begin(), slot.end(), -1);
+        // bounding box of the part (the loops below visit nothing else)
+        int blo[3] = {lo, lo, lo}, bhi[3] = {hi, hi, hi};  // x, y, z
+        for (int b = 0; b < nbits; b++) {
+            if ((part >> b) & 1) bhi[2 - b] = 0;
+            else blo[2 - b] = 0;
+        }
         // pass 1: level sizes and slots (rank inside the level; rate-receiving cells first, then lexicographic)
         std::vector<int> count(nlevels, 0), nfirst(nlevels, 0), fill_a(nlevels, 0), fill_b(nlevels, 0);
-        for (int i = lo; i <= hi; i++)
-            for (int j = lo; j <= hi; j++)
-                for (int k = lo; k <= hi; k++) {
+        for (int i = blo[0]; i <= bhi[0]; i++)
+            for (int j = blo[1]; j <= bhi[1]; j++)
+                for (int k = blo[2]; k <= bhi[2]; k++) {
                     bool owned;
-                    if (!member(i, j, k) || !in_part(part, i, j, k, owned)) continue;
+                    if (!in_part(part, i, j, k, owned) || !member(i, j, k)) continue;
                     const int m = level_of(i, j, k);
                     count[m]++;
                     if (owned && rated(i, j, k)) nfirst[m]++;
                 }
-        for (int i = lo; i <= hi; i++)
-            for (int j = lo; j <= hi; j++)
-                for (int k = lo; k <= hi; k++) {
+        for (int i = blo[0]; i <= bhi[0]; i++)
+            for (int j = blo[1]; j <= bhi[1]; j++)
+                for (int k = blo[2]; k <= bhi[2]; k++) {
                     bool owned;
-                    if (!member(i, j, k) || !in_part(part, i, j, k, owned)) continue;
+                    if (!in_part(part, i, j, k, owned) || !member(i, j, k)) continue;
                     const int m = level_of(i, j, k);
                     slot[sidx(i, j, k)] = (owned && rated(i, j, k)) ? fill_a[m]++ : nfirst[m] + fill_b[m]++;
                 }
@@ -209,11 +239,11 @@ bool build_sweep_plan(SweepPlan& plan, int N, double R, double dr, bool sphere_o
         }
         plan.cells.resize((size_t)ls[nlevels]);
         // pass 2: geometry
-        for (int i = lo; i <= hi; i++)
-            for (int j = lo; j <= hi; j++)
-                for (int k = lo; k <= hi; k++) {
+        for (int i = blo[0]; i <= bhi[0]; i++)
+            for (int j = blo[1]; j <= bhi[1]; j++)
+                for (int k = blo[2]; k <= bhi[2]; k++) {
                     bool owned;
-                    if (!member(i, j, k) || !in_part(part, i, j, k, owned)) continue;
+                    if (!in_part(part, i, j, k, owned) || !member(i, j, k)) continue;
                     const int ia = std::abs(i), ja = std::abs(j), ka = std::abs(k);
                     const int m = level_of(i, j, k);
                     PlanCell pc;

@@ -63,7 +63,7 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
             # shard by position: planes of the slowest axis with equal source counts (parallel.py)
             edges, h = slab_edges(np.asarray(src_pos)[0] - 1, N, nprocs, R_max_LLS)
             if edges is None and decomposition == "slab":
-                raise ValueError("slab decomposition impossible: a slab would be thinner than two halos")
+                raise ValueError("slab decomposition impossible: a halo does not fit the neighbouring slab")
         if edges is not None:
             halo = SlabHalo(edges, h, N, rank, nprocs, group)
             x0 = np.mod(np.asarray(src_pos)[0].astype(np.int64) - 1, N)

@@ -75,11 +75,13 @@ def device_tensor(ptr, n):
 # with their two neighbours (23 MB each at 512^3, R = 10.76) and all-reduce three scalars.
 
 def slab_edges(src_x0, N, nprocs, R):
-    """Plane ranges [edges[r], edges[r+1]) with (nearly) equal source counts, or None when a slab would be thinner
-    than two halos (then the list-order sharding with an all-reduce is used).  ``src_x0``: 0-indexed x of every
-    source.  Deterministic, so every rank computes the same edges."""
+    """Plane ranges [edges[r], edges[r+1]) with (nearly) equal source counts, or None when the slabs would be too thin
+    (then the list-order sharding with an all-reduce is used): a halo must fit inside the neighbouring slab (width >= h)
+    and a slab with both its halos must not meet itself around the box (width + 2h <= N; with two ranks, where both
+    neighbours are the same rank, this is the familiar "two halos wide").  ``src_x0``: 0-indexed x of every source.
+    Deterministic, so every rank computes the same edges."""
     h = int(np.floor(R)) + 1
-    if nprocs < 2 or 2 * h * nprocs > N:
+    if nprocs < 2 or h * nprocs > N or (N + nprocs - 1) // nprocs + 2 * h > N:
         return None, h
     xs = np.sort(np.mod(np.asarray(src_x0, dtype=np.int64), N))
     edges = [0]
@@ -87,12 +89,18 @@ def slab_edges(src_x0, N, nprocs, R):
         e = int(xs[(r * xs.size) // nprocs]) if xs.size else (r * N) // nprocs
         edges.append(e)
     edges.append(N)
-    # enforce a minimum width of 2h by pushing edges apart (left to right, then right to left)
+    # enforce the minimum width by pushing edges apart (left to right, then right to left), then the maximum width
+    wmin, wmax = h, N - 2 * h
     for r in range(1, nprocs):
-        edges[r] = max(edges[r], edges[r - 1] + 2 * h)
+        edges[r] = max(edges[r], edges[r - 1] + wmin)
     for r in range(nprocs - 1, 0, -1):
-        edges[r] = min(edges[r], edges[r + 1] - 2 * h)
-    if any(edges[r + 1] - edges[r] < 2 * h for r in range(nprocs)):
+        edges[r] = min(edges[r], edges[r + 1] - wmin)
+    for r in range(1, nprocs):
+        edges[r] = min(edges[r], edges[r - 1] + wmax)
+    for r in range(nprocs - 1, 0, -1):
+        edges[r] = max(edges[r], edges[r + 1] - wmax)
+    widths = [edges[r + 1] - edges[r] for r in range(nprocs)]
+    if min(widths) < wmin or max(widths) > wmax:
         return None, h
     return edges, h
 

@@ -224,15 +224,18 @@ def test_slab_edges():
     assert h == 11 and edges[0] == 0 and edges[-1] == 256 and len(edges) == 9
     counts = [np.sum((x >= edges[r]) & (x < edges[r + 1])) for r in range(8)]
     assert sum(counts) == 10000 and max(counts) - min(counts) < 300
-    assert all(edges[r + 1] - edges[r] >= 2 * h for r in range(8))
-    assert slab_edges(x, 256, 8, 30.0)[0] is None            # 8 slabs of 32 planes cannot hold two 31-plane halos
+    assert all(edges[r + 1] - edges[r] >= h for r in range(8))
+    e30, h30 = slab_edges(x, 256, 8, 30.0)                   # 8 slabs of ~32 planes, 31-plane halos inside the neighbours
+    assert h30 == 31 and all(31 <= e30[r + 1] - e30[r] <= 256 - 62 for r in range(8))
+    assert slab_edges(x, 256, 8, 32.0)[0] is None            # a 33-plane halo does not fit a 32-plane neighbour
+    assert slab_edges(x, 256, 2, 64.0)[0] is None            # two ranks: a slab and its two halos would meet themselves
     assert slab_edges(x, 256, 1, 5.0)[0] is None
     clustered = np.full(1000, 17)
     e2, h2 = slab_edges(clustered, 128, 2, 4.5)               # all sources in one plane: widths are enforced
-    assert e2 is not None and all(e2[r + 1] - e2[r] >= 2 * h2 for r in range(2))
+    assert e2 is not None and all(h2 <= e2[r + 1] - e2[r] <= 128 - 2 * h2 for r in range(2))
 
 
-def _slab_rank_main(rank, world, port, outdir):
+def _slab_rank_main(rank, world, port, outdir, R=3.3):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -244,7 +247,7 @@ def _slab_rank_main(rank, world, port, outdir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     c = make_case("multi_n32")
-    N, R = c["N"], 3.3
+    N = c["N"]
     x0 = c["srcpos"][0] - 1
     edges, h = slab_edges(x0, N, world, R)
     halo = SlabHalo(edges, h, N, rank, world)
@@ -266,18 +269,18 @@ def _slab_rank_main(rank, world, port, outdir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_slab_decomposition_over_gloo(tmp_path, world):
+@pytest.mark.parametrize("world,R", [(2, 3.3), (3, 3.3), (3, 7.3)])   # the last: slabs thinner than two halos
+def test_slab_decomposition_over_gloo(tmp_path, world, R):
     """Slab-sharded sources + halo reduction of the rates + assembly == single-process result; the xh_av halo gather
     delivers the neighbours' planes.  CPU ranks over gloo, the oracle standing in for the GPU sweep."""
     import torch.multiprocessing as mp
     import oracle
     from tests.fields import make_case
     port = _free_port()
-    mp.spawn(_slab_rank_main, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_slab_rank_main, args=(world, port, str(tmp_path), R), nprocs=world, join=True)
     c = make_case("multi_n32")
     N = c["N"]
-    ref, _, _ = oracle.asora_do_all_sources(3.3, c["sig"], c["dr"], c["ndens"].ravel(), c["xh"].ravel(), c["pos_flat"],
+    ref, _, _ = oracle.asora_do_all_sources(R, c["sig"], c["dr"], c["ndens"].ravel(), c["xh"].ravel(), c["pos_flat"],
                                             c["flux_flat"], N, c["thin"], c["thick"], c["minlogtau"], c["dlogtau"], c["NumTau"])
     e = np.load(tmp_path / "edges_0.npy")
     edges, h = list(e[:-1]), int(e[-1])

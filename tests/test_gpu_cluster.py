@@ -68,7 +68,8 @@ def test_cluster_column_density_vs_oracle(name):
 
 def test_cluster_full_box_128_vs_reference_kernel():
     """Full 128^3 box (q_max = 193 clipped to 65 levels), 6 sources on non-trivial fields, per cell against the reference's
-    own kernel (oracle/_ref) and the oracle; automatic variant selection must pick the cluster sweep."""
+    own kernel (oracle/_ref) and the oracle; also the eight-octant shared-memory sweep, which the automatic selection
+    picks for four or more sources while an octant's levels fit one SM."""
     from pyc2ray_b200.lib import _cabi, libasora
     from tests.fields import f1_fields, tables, SIG
     from tests.test_gpu_parity import _setup, _sweep, _assert_close
@@ -85,13 +86,17 @@ def test_cluster_full_box_128_vs_reference_kernel():
              NumTau=numtau, pos_flat=pos_flat, flux_flat=flux_flat)
     _setup(libasora, c)
     try:
-        phi, used, upd = _sweep(libasora, _cabi, c, 0)
+        phi, used, upd = _sweep(libasora, _cabi, c, 4)
         assert used == 4 and upd == ns * N ** 3
         grid, used2, _ = _sweep(libasora, _cabi, c, 2)
         assert used2 == 2
+        # q_max > 127: the shared-memory sweep in its eight-octant form (what many sources at such radii get)
+        octs, used1, upd1 = _sweep(libasora, _cabi, c, 0)
+        assert used1 == 1 and upd1 == upd
     finally:
         libasora.device_close()
     _assert_close(phi, grid, "cluster sweep vs grid-cooperative sweep, full 128^3 box", rtol=1e-11)
+    _assert_close(phi, octs, "cluster sweep vs eight-octant shared-memory sweep, full 128^3 box", rtol=1e-11)
     ref, _, n = _oracle(c)
     _assert_close(phi, ref, "cluster sweep vs oracle, full 128^3 box")
     if os.path.exists(REF_SO):
