@@ -47,7 +47,7 @@ struct Context {
     double* nhi = nullptr;      // ndens * (1 - xh_av) * sigma * dr, rebuilt before every sweep
     double* phi_keep = nullptr; // rates of earlier sweeps while a sweep accumulates on top of them (zero_phi = 0)
     // pageable host buffers: per-thread pinned bounce buffers and streams of host_copy()
-    static constexpr int kCopyThreads = 4;
+    static constexpr int kCopyThreads = 16;   // upper bound; copy_threads() picks how many are used
     static constexpr size_t kBounceBytes = (size_t)4 << 20;
     char* bounce[kCopyThreads][2] = {{nullptr}};
     cudaStream_t copy_stream[kCopyThreads] = {nullptr};
@@ -164,6 +164,22 @@ int ensure_buffer(int which)
     return 0;
 }
 
+// Staging threads of host_copy(): ASORA_COPY_THREADS, else half the host threads this process may run on, 4 to 8.
+int copy_threads()
+{
+    static int n = 0;
+    if (n == 0) {
+        const char* env = std::getenv("ASORA_COPY_THREADS");
+        int v = env ? std::atoi(env) : 0;
+        if (v <= 0) {
+            v = (int)std::thread::hardware_concurrency() / 2;
+            v = std::max(4, std::min(8, v));
+        }
+        n = std::max(1, std::min(Context::kCopyThreads, v));
+    }
+    return n;
+}
+
 // Host <-> device copy of a whole grid.  Pinned host memory goes straight to the copy engine.  Pageable memory
 // (what numpy hands over) would be staged by the driver on one thread at ~11 GB/s (measured: 11 ms per 125 MB grid,
 // five grids per evolve3D call); here kCopyThreads host threads stage disjoint slices through their own pinned
@@ -184,7 +200,7 @@ int host_copy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind)
         CK(cudaStreamSynchronize(g.stream));
         return 0;
     }
-    const int T = Context::kCopyThreads;
+    const int T = copy_threads();
     const size_t B = Context::kBounceBytes;
     for (int t = 0; t < T; t++) {
         if (!g.copy_stream[t]) CK(cudaStreamCreateWithFlags(&g.copy_stream[t], cudaStreamNonBlocking));

@@ -250,6 +250,8 @@ __device__ __forceinline__ double finish_cell_pre(double tau_in, double path_cel
         const double absorbed = thick ? (t_in - t_out) : dtau * t_out;
         deposit_rate<DET>(p.phi_ion, p.det_lo, p.det_scale, pos, skn * absorbed);
         if (HEAT) {  // photorates.f90:118,124 + raytracing.f90:530,537, same prefactor and the same deferred / nHI
+            // Thin cells: the heating table is read at tau_out, the convention of the ASORA ionisation rate above
+            // (rates.cu:36), not at tau_in as in photorates.f90:124; the two differ by O(dtau) <= 1e-7 relative.
             const double heated = thick ? (h_in - h_out) : dtau * h_out;
             deposit_rate<DET>(p.phi_heat, p.det_lo_heat, p.det_scale_heat, pos, skn * heated);
         }
