@@ -135,6 +135,7 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
     s1 = ctypes.c_double(0.0)
     s0 = ctypes.c_double(0.0)
     t_loop0 = time.perf_counter()
+    phases = {"sweep": 0.0, "exchange_phi": 0.0, "chemistry": 0.0, "exchange_xh": 0.0}  # seconds, summed over the iterations
     try:
         # process-global sweep settings: switched on inside the try so that the finally below always resets them
         # The evolve loop only consumes phi_ion, so the sweep may skip the cells outside the R_max sphere
@@ -145,9 +146,12 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
         while not converged:
             niter += 1
             trt0 = time.time()
+            trt0p = time.perf_counter()
             check(L.asora_raytrace_device(float(R_max_LLS), float(sig), float(dr), 0, NumSrc, float(minlogtau),
                                           float(dlogtau), int(NumTau), 1))
             check(L.asora_sync())
+            tph = time.perf_counter()
+            phases["sweep"] += tph - trt0p
             if nprocs > 1:
                 torch.cuda.nvtx.range_push("asora:exchange_phi")
             if halo is not None:
@@ -162,18 +166,24 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
             if nprocs > 1:
                 torch.cuda.nvtx.range_pop()
             trt = time.time() - trt0
+            phases["exchange_phi"] += time.perf_counter() - tph
             tch0 = time.time()
+            tch0p = time.perf_counter()
             if halo is not None:
                 o, cnt = halo.own_cells()
                 check(L.asora_global_pass_device_range(float(dt), float(bh00), float(albpow), float(colh0), float(temph0),
                                                        float(abu_c), o, cnt, ctypes.byref(flag), ctypes.byref(s1),
                                                        ctypes.byref(s0)))
+                phases["chemistry"] += time.perf_counter() - tch0p
+                tch0p = time.perf_counter()
                 scal.copy_(torch.tensor([flag.value, s1.value, s0.value], dtype=torch.float64))
                 allreduce_sum_(scal, group)   # conv_flag, sum x, sum 1-x over all planes
                 halo.gather_xh_(xav_t)        # my neighbours' new xh_av inside my ray-tracing reach
                 torch.cuda.synchronize()
                 g = scal.tolist()
                 conv_flag, sum_xh1_int, sum_xh0_int = int(round(g[0])), g[1], g[2]
+                phases["exchange_xh"] += time.perf_counter() - tch0p
+                tch0p = None
             elif rsag:
                 check(L.asora_global_pass_device_range(float(dt), float(bh00), float(albpow), float(colh0), float(temph0),
                                                        float(abu_c), rank * chunk, chunk, ctypes.byref(flag), ctypes.byref(s1),
@@ -189,6 +199,8 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
                                                  float(abu_c), ctypes.byref(flag), ctypes.byref(s1), ctypes.byref(s0)))
                 conv_flag, sum_xh1_int, sum_xh0_int = flag.value, s1.value, s0.value
             tch = time.time() - tch0
+            if tch0p is not None:
+                phases["chemistry"] += time.perf_counter() - tch0p
             # evolve.py:216-232
             rel_change_xh1 = abs((sum_xh1_int - prev_sum_xh1_int) / sum_xh1_int) if sum_xh1_int > 0.0 else 1.0
             rel_change_xh0 = abs((sum_xh0_int - prev_sum_xh0_int) / sum_xh0_int) if sum_xh0_int > 0.0 else 1.0
@@ -206,6 +218,7 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
         L.asora_set_sphere_only(0)
         L.asora_set_active_slab(0, 0)
     evolve3D.last_loop_seconds = time.perf_counter() - t_loop0  # the convergence loop alone: no host<->device grid copies
+    evolve3D.last_phase_seconds = phases
     if rsag:
         # once per time step: every rank gets the whole grids back (the reference API returns full arrays)
         allgather_chunks_(device_tensor(L.asora_device_buffer(_cabi.BUF_XH_INTERMED), NumCells), rank, nprocs, group)
@@ -293,3 +306,4 @@ def evolve3D_MPI(dt, dr, src_flux, src_pos, use_gpu, max_subbox, subboxsize, los
         raise RuntimeError("evolve3D_MPI: initialise torch.distributed (backend='nccl') with the same rank/size")
     return evolve3D_dist(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table, photo_thick_table, minlogtau,
                          dlogtau, R_max_LLS, convergence_fraction, sig, bh00, albpow, colh0, temph0, abu_c, logfile, quiet)
+evolve3D.last_phase_seconds = {}
