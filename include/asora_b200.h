@@ -214,6 +214,13 @@ int asora_set_sphere_only(int sphere_only);
  * path.  Default 0. */
 int asora_set_deterministic(int on);
 
+/* The reference's -D GREY_NOTABLES build (src/asora/Makefile:9 comment, raytracing.cu:317-318, rates.cu:44-64; Fortran:
+ * raytracing.f90:499-501, photorates.f90:13-57): with on != 0 the rate of a cell is the analytic grey-opacity expression
+ * strength * 1e48 / Vfact * (exp(-tau_in) - exp(-tau_out)) (thin cells: (tau_out - tau_in) * exp(-tau_in)) instead of the
+ * table lookups; the uploaded tables are ignored and need not exist.  A test option, as in the reference: such sweeps run
+ * on the grid-cooperative variant, without heating and without the deterministic mode.  Reset by device_close. */
+int asora_set_grey_notables(int on);
+
 /* Override the launch shape of the shared-memory sweep: sources per CTA (1 or 2) and, in the low 16 bits of
  * block_threads, threads per CTA (256, 512, 768, 896 or 1024 for one source; 256, 512 or 1024 for two); 0 =
  * automatic.  Bits 16-18 of block_threads toggle launch options against their automatic choice (copies of the

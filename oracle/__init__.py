@@ -29,6 +29,7 @@ ASORA = 1
 OPT_NORMFLUX_BUG = 1
 OPT_USE_SUBBOX = 2
 OPT_FMA_DIST2 = 4
+OPT_GREY_NOTABLES = 8   # -DGREY_NOTABLES: analytic grey-opacity rates (rates.cu:48-64, photorates.f90:13-57)
 
 _lib = None
 
@@ -106,7 +107,7 @@ def asora_do_all_sources_heat(R, sig, dr, ndens_flat, xh_av_flat, srcpos_flat, s
 
 
 def asora_do_all_sources(R, sig, dr, ndens_flat, xh_av_flat, srcpos_flat, srcflux, N, thin, thick,
-                         minlogtau, dlogtau, NumTau, fma_dist2=True, nthreads=1):
+                         minlogtau, dlogtau, NumTau, fma_dist2=True, nthreads=1, grey_notables=False):
     """CPU restatement of libasora.do_all_sources (src/asora/raytracing.cu:79-148).
 
     Inputs use the ASORA wire format: flat C-ordered float64 grids, int32 interleaved 0-indexed
@@ -124,7 +125,7 @@ def asora_do_all_sources(R, sig, dr, ndens_flat, xh_av_flat, srcpos_flat, srcflu
     phi = np.zeros(n3)
     cdh = np.zeros(n3)
     stats = np.zeros(2)
-    opts = OPT_FMA_DIST2 if fma_dist2 else 0
+    opts = (OPT_FMA_DIST2 if fma_dist2 else 0) | (OPT_GREY_NOTABLES if grey_notables else 0)
     n = lib().oracle_do_all_sources(ASORA, opts, _dp(flux), pos.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
                                     flux.size, N, float(R), float(sig), float(dr), _dp(ndens_flat),
                                     _dp(xh_av_flat), _dp(phi), _dp(cdh), _dp(thin), _dp(thick), thin.size,
@@ -134,7 +135,7 @@ def asora_do_all_sources(R, sig, dr, ndens_flat, xh_av_flat, srcpos_flat, srcflu
 
 def fortran_do_all_sources(normflux, srcpos, max_subbox, subboxsize, sig, dr, ndens, xh_av, loss_fraction,
                            thin, thick, minlogtau, dlogtau, R_max_LLS, NumTau=None, use_subbox=True,
-                           normflux_bug=False, nthreads=1, heat_thin=None, heat_thick=None):
+                           normflux_bug=False, nthreads=1, heat_thin=None, heat_thick=None, grey_notables=False):
     """CPU restatement of libc2ray.raytracing.do_all_sources (src/c2ray/raytracing.f90:52-119).
 
     srcpos is (3, NumSrc), 1-indexed; ndens / xh_av are (N,N,N) logical arrays (any memory order; they
@@ -153,7 +154,8 @@ def fortran_do_all_sources(normflux, srcpos, max_subbox, subboxsize, sig, dr, nd
     phi = np.zeros((N, N, N), order="F")
     cdh = np.zeros((N, N, N), order="F")
     stats = np.zeros(2)
-    opts = (OPT_USE_SUBBOX if use_subbox else 0) | (OPT_NORMFLUX_BUG if normflux_bug else 0)
+    opts = ((OPT_USE_SUBBOX if use_subbox else 0) | (OPT_NORMFLUX_BUG if normflux_bug else 0) |
+            (OPT_GREY_NOTABLES if grey_notables else 0))
     if heat_thin is not None:
         # with heating tables: returns phi_heat as a sixth value (raytracing.f90:52-110 fills it in place)
         ht = np.ascontiguousarray(heat_thin, dtype=np.float64)

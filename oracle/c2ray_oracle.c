@@ -47,6 +47,7 @@
 #define ORACLE_OPT_NORMFLUX_BUG 1 /* raytracing.f90:500,503 uses normflux(NumSrc) for every source */
 #define ORACLE_OPT_USE_SUBBOX 2   /* -DUSE_SUBBOX (src/c2ray/Makefile:3) */
 #define ORACLE_OPT_FMA_DIST2 4    /* nvcc contracts xs*xs+ys*ys+zs*zs (raytracing.cu:305) into FMAs */
+#define ORACLE_OPT_GREY_NOTABLES 8 /* -DGREY_NOTABLES: analytic grey-opacity rates (rates.cu:48-64, photorates.f90:13-57) */
 
 typedef struct {
     double sqrt3, sqrt2;    /* raytracing.f90:608-609 vs raytracing.cu:435,439 */
@@ -54,6 +55,7 @@ typedef struct {
     double max_coldensh;    /* raytracing.f90:368 vs raytracing.cu:15 */
     int thin_uses_tau_out;  /* rates.cu:37 (tau_out) vs photorates.f90:121 (tau_in) */
     int fma_dist2;
+    int grey_notables;      /* raytracing.cu:317-318, raytracing.f90:499-501 */
 } consts_t;
 
 static consts_t make_consts(int flavour, int opts)
@@ -74,6 +76,7 @@ static consts_t make_consts(int flavour, int opts)
         c.thin_uses_tau_out = 1;
         c.fma_dist2 = (opts & ORACLE_OPT_FMA_DIST2) ? 1 : 0;
     }
+    c.grey_notables = (opts & ORACLE_OPT_GREY_NOTABLES) ? 1 : 0;
     return c;
 }
 
@@ -112,8 +115,23 @@ static double photoion_rates(const consts_t *c, double normflux, double coldens_
     double tau_in = coldens_in * sig;
     double tau_out = coldens_out * sig;
     double prefact = normflux / Vfact;
-    double phi_photo_in = prefact * photo_lookuptable(thick, tau_in, minlogtau, dlogtau, NumTau, ntab);
-    double cell;
+    double phi_photo_in, cell;
+    if (c->grey_notables) {
+        /* photoion_rates_test_gpu (rates.cu:48-64) == photoion_rates_test (photorates.f90:13-57): no tables, the
+         * source strength in units of S_STAR_REF = 1e48 (rates.cu:8); the thin branch uses exp(-tau_in) in both */
+        prefact = normflux * 1e48 / Vfact;
+        phi_photo_in = prefact * exp(-tau_in);
+        if (fabs(tau_out - tau_in) > c->tau_photo_limit) {
+            double phi_photo_out = prefact * exp(-tau_out);
+            cell = phi_photo_in - phi_photo_out;
+            if (phi_out) *phi_out = phi_photo_out;
+        } else {
+            cell = prefact * (tau_out - tau_in) * exp(-tau_in);
+            if (phi_out) *phi_out = phi_photo_in - cell;
+        }
+        return cell;
+    }
+    phi_photo_in = prefact * photo_lookuptable(thick, tau_in, minlogtau, dlogtau, NumTau, ntab);
     if (fabs(tau_out - tau_in) > c->tau_photo_limit) {
         double phi_photo_out = prefact * photo_lookuptable(thick, tau_out, minlogtau, dlogtau, NumTau, ntab);
         cell = phi_photo_in - phi_photo_out;

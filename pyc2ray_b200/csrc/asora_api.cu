@@ -89,6 +89,7 @@ struct Context {
     int slab_begin = 0, slab_count = 0;  // active planes of a slab-decomposed run (0 = whole grid)
     int sphere_only = 0;
     int deterministic = 0;            // asora_set_deterministic: fixed-point accumulation of the rates
+    int grey = 0;                     // asora_set_grey_notables: analytic grey-opacity rates instead of the tables
     long long* det_lo = nullptr;      // low parts of the fixed-point sums (N^3), and of the heating sums
     long long* det_lo_heat = nullptr;
     double flux_max = 0.0;            // largest uploaded source flux
@@ -309,7 +310,9 @@ SweepPlan* get_plan(int N, double R, double dr, bool sphere_only, bool octant, i
 int run_sweep(double R, double sig, double dr, int begin, int count, double minlogtau, double dlogtau,
               int NumTau, bool zero_phi, double* coldens_grid)
 {
-    if (!g.thin || !g.thick) return fail("photo tables not on device: call photo_table_to_device first");
+    if (!g.grey && (!g.thin || !g.thick)) return fail("photo tables not on device: call photo_table_to_device first");
+    if (g.grey && (g.heating || g.deterministic))
+        return fail("grey-opacity test rates (set_grey_notables) exist without heating and without the deterministic mode only");
     if (begin < 0 || count < 0 || begin + count > g.nsrc)
         return fail("source range exceeds the list uploaded with source_data_to_device");
     if (int rc = ensure_buffer(ASORA_BUF_NDENS)) return rc;
@@ -334,6 +337,7 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     p.sig = sig;
     p.dr = dr;
     p.kpref = (sig * dr) / (ASORA_FOURPI * (dr * dr * dr));
+    p.grey = g.grey;
     p.tau_max = sig * ASORA_MAX_COLDENSH;
     // rates.cu:77-78: index = 1 + (log10(tau) - minlogtau)/dlogtau = lut_a + lut_b * log2(tau)
     p.lut_b = 0.30102999566398119521 / dlogtau;
@@ -412,6 +416,7 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     // one plan entry and up to eight octant images per thread (sweep_octant.cu), for mirror-symmetric cell sets;
     // 2: grid-cooperative sweep through L2 scratch grids when a level does not fit in shared memory.
     int variant = g.variant_forced;
+    if (g.grey) variant = 2;  // the analytic test rates exist in the grid-cooperative sweep only (any mesh, any radius)
     int S = 1, block = 256, opts = 0;
     int noct = 8, opt = 8, batch = 4;
     SweepPlan* plan = nullptr;
@@ -806,6 +811,7 @@ int asora_device_close(void)
     g.grid_max_groups = 0;
     g.cells_N = 0;
     g.slab_begin = g.slab_count = 0;
+    g.grey = 0;
     if (g.log2_tab) cudaFree(g.log2_tab);
     g.nhi = nullptr;
     g.log2_tab = nullptr;
@@ -1328,6 +1334,13 @@ int64_t asora_plan_export(int N, double R, double dr, int sphere_only, int octan
         if (level_mid) std::copy(plan.level_mid.begin(), plan.level_mid.end(), level_mid);
     }
     return n;
+}
+
+int asora_set_grey_notables(int on)
+{
+    if (int rc = need_init()) return rc;
+    g.grey = on ? 1 : 0;
+    return 0;
 }
 
 int asora_set_deterministic(int on)

@@ -23,6 +23,7 @@
 #define ASORA_SQRT2 1.41421356237                       // raytracing.cu:439
 #define ASORA_MAX_COLDENSH 2e30                         // raytracing.cu:15
 #define ASORA_TAU_PHOTO_LIMIT 1.0e-7                    // src/asora/rates.cu:7
+#define ASORA_S_STAR_REF 1e48                           // src/asora/rates.cu:8 (used by the grey-opacity test rates only)
 
 // Most concurrent sources (CTA groups, one scratch grid each) of the grid-cooperative sweep
 #define ASORA_GRID_GROUPS_MAX 74
@@ -97,6 +98,7 @@ struct SweepParams {
     const double* src_flux;
     int src_begin, src_count;
     int sphere_only;          // grid-cooperative variant: skip cells outside the R sphere
+    int grey;                 // analytic grey-opacity rates (the reference's -D GREY_NOTABLES build), grid-cooperative variant
     unsigned zface_offset;    // != 0: z-face cells use the (k,i,j)-ordered copies of nhi / phi this many doubles behind them
     // deterministic accumulation (asora_set_deterministic): phi_ion / phi_heat then hold the high parts and det_lo /
     // det_lo_heat the low parts of 128-bit fixed-point sums, see deposit_rate in sweep_device.cuh; det_scale == 0: off

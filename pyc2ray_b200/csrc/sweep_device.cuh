@@ -231,7 +231,8 @@ __device__ __forceinline__ void deposit_rate(double* __restrict__ grid, long lon
 }
 
 // skn = strength * kpref * inv_np.
-template <int REP, bool TEX, bool HEAT, bool DET = false>
+// GREY: the reference's -D GREY_NOTABLES build (raytracing.cu:317-318): analytic grey-opacity rates instead of the tables.
+template <int REP, bool TEX, bool HEAT, bool DET = false, bool GREY = false>
 __device__ __forceinline__ double finish_cell_pre(double tau_in, double path_cells, double skn, unsigned flags,
                                                   double ntau_p, size_t pos, const SweepParams& p,
                                                   const double2* __restrict__ log2_tab)
@@ -240,6 +241,14 @@ __device__ __forceinline__ double finish_cell_pre(double tau_in, double path_cel
     if ((flags & PC_RATED) && tau_in <= p.tau_max) {  // coldensh_in <= MAX_COLDENSH (raytracing.cu:315)
         const double dtau = tau_out - tau_in;
         const bool thick = fabs(dtau) > ASORA_TAU_PHOTO_LIMIT;
+        if (GREY) {
+            // photoion_rates_test_gpu (rates.cu:48-64): strength * S_STAR_REF / Vfact * (exp(-tau_in) - exp(-tau_out)), thin
+            // cells (tau_out - tau_in) * exp(-tau_in); the division by nHI is deferred like that of the table rates
+            const double e_in = exp(-tau_in);
+            const double absorbed = thick ? (e_in - exp(-tau_out)) : dtau * e_in;
+            deposit_rate<false>(p.phi_ion, nullptr, 0.0, pos, (skn * ASORA_S_STAR_REF) * absorbed);
+            return tau_out;
+        }
         // Beyond the end of the table both lookups of a thick cell are clamped to the same entry (rates.cu:78-79), so the
         // reference adds exactly T - T = 0 there: nothing to look up or deposit.  In an optically thick box that is most
         // of a large-radius sweep (tau reaches 10^4 within 44 cells of a source in the reference's benchmark field).
@@ -259,10 +268,10 @@ __device__ __forceinline__ double finish_cell_pre(double tau_in, double path_cel
     return tau_out;
 }
 
-template <int REP, bool TEX, bool HEAT, bool DET = false>
+template <int REP, bool TEX, bool HEAT, bool DET = false, bool GREY = false>
 __device__ __forceinline__ double finish_cell(double tau_in, double path_cells, double inv_np, unsigned flags,
                                               double ntau_p, double sk, size_t pos, const SweepParams& p,
                                               const double2* __restrict__ log2_tab)
 {
-    return finish_cell_pre<REP, TEX, HEAT, DET>(tau_in, path_cells, sk * inv_np, flags, ntau_p, pos, p, log2_tab);
+    return finish_cell_pre<REP, TEX, HEAT, DET, GREY>(tau_in, path_cells, sk * inv_np, flags, ntau_p, pos, p, log2_tab);
 }

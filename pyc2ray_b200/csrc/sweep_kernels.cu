@@ -374,7 +374,7 @@ __device__ __forceinline__ void group_barrier(unsigned* counter, unsigned nctas,
 // The grid is split into `ngroups` groups of `group_ctas` CTAs; group g sweeps sources g, g+ngroups, ...
 // through its own N^3 scratch grid, so that sources whose levels are much narrower than the GPU run
 // side by side.  ngroups == 1 is "the whole GPU per source".
-template <bool HEAT, bool DET>
+template <bool HEAT, bool DET, bool GREY = false>
 __global__ void __launch_bounds__(512, 2)
 sweep_grid_kernel(SweepParams p, int nlevels, int ngroups, int group_ctas, unsigned* counters)
 {
@@ -468,7 +468,7 @@ sweep_grid_kernel(SweepParams p, int nlevels, int ngroups, int group_ctas, unsig
                     const double c4 = ((1.0 - wA) * (1.0 - wB) != 0.0) ? __ldcg(slab + q4) : 0.0;
                     cin = interp_coldens<true, true>(c1, c2, c3, c4, wA, wB, flags);
                 }
-                const double cdho = finish_cell<1, false, HEAT, DET>(cin, path, inv_np, flags, nHI_p, sk, pos, p, log2_tab);
+                const double cdho = finish_cell<1, false, HEAT, DET, GREY>(cin, path, inv_np, flags, nHI_p, sk, pos, p, log2_tab);
                 __stcg(slab + pos, cdho);
             }
             group_barrier(counter, (unsigned)group_ctas, epoch);
@@ -488,7 +488,10 @@ int sweep_grid_groups(const SweepParams& p, int max_groups, int* total_ctas_out,
         int dev = 0, sms = 0, per_sm = 0;
         if (cudaGetDevice(&dev) != cudaSuccess) return 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        int per_sm_grey = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_grid_kernel<true, true>, block, 0) != cudaSuccess) return 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_grey, sweep_grid_kernel<false, false, true>, block, 0) != cudaSuccess) return 0;
+        per_sm = min(per_sm, per_sm_grey);
         if (per_sm < 1) return 0;
         total_cached = sms * per_sm;
     }
@@ -524,6 +527,10 @@ cudaError_t launch_sweep_grid(const SweepParams& p, int ngroups, unsigned* count
     if (launches) *launches += 1;
     void* kernel = pc.det_lo ? (pc.phi_heat ? (void*)sweep_grid_kernel<true, true> : (void*)sweep_grid_kernel<false, true>)
                              : (pc.phi_heat ? (void*)sweep_grid_kernel<true, false> : (void*)sweep_grid_kernel<false, false>);
+    if (pc.grey) {
+        if (pc.det_lo || pc.phi_heat) return cudaErrorNotSupported;
+        kernel = (void*)sweep_grid_kernel<false, false, true>;
+    }
     return cudaLaunchCooperativeKernel(kernel, dim3(total), dim3(block), args, 0, stream);
 }
 

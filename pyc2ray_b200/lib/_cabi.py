@@ -51,6 +51,7 @@ SIGNATURES = {
     "asora_set_tuning": (_i, [_i, _i]),
     "asora_set_sphere_only": (_i, [_i]),
     "asora_set_deterministic": (_i, [_i]),
+    "asora_set_grey_notables": (_i, [_i]),
     "asora_set_octant_shape": (_i, [_i, _i, _i, _i]),
     "asora_set_cluster_shape": (_i, [_i, _i]),
     "asora_plan_builds": (_i, []),
