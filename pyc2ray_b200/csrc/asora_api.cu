@@ -423,11 +423,12 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     const int hi_cells = std::min(p.q_max, std::max(-p.last_l, p.last_r));
     const bool symmetric = std::min(p.q_max, p.last_r) == std::min(p.q_max, -p.last_l) && hi_cells <= 126;
     const size_t budget = (size_t)g.smem_optin;
-    // automatic choice (measured, scripts/octant_probe.py, profiles/r02f_radius_sweep_256.md): the mirror-image sweep wins on
-    // full-octahedron sweeps whose eight octants just fit one SM (R = 30: 16.3 vs 17.0 ms for 10^4 sources); smaller
-    // radii, larger radii (split sweeps) and sphere-only sweeps stay on variant 1 (R = 20: 5.7 vs 7.2 ms; R = 40: 10.7 vs
-    // 11.6 ms; R = 30 sphere-only: 11.2 vs 11.9 ms; R = 10.76: 8.4 vs 11.3 ms)
-    const bool auto_octant = !sphere_only && hi_cells >= 44 && hi_cells <= 60 && !g.heating;
+    // automatic choice (measured, scripts/octant_probe.py, profiles/r02f_radius_sweep_256.md, bench field): the mirror-image
+    // sweep wins on sweeps whose eight octants just fit one SM -- full octahedron, 44 <= q_max <= 60: R = 25 9.7 vs 10.6 ms,
+    // R = 30 14.5 vs 17.0 ms, R = 34 20.2 vs 26.8 ms (10^4 sources); sphere only from q_max = 50: R = 30 11.1 vs 11.5 ms,
+    // R = 34 15.5 vs 16.6 ms, but R = 25 7.3 vs 7.0 ms.  Smaller radii and larger ones (split sweeps) stay on variant 1
+    // (R = 20: 52.1 vs 54.0 ms for 10^5 sources; R = 40: 10.7 vs 11.6 ms).
+    const bool auto_octant = hi_cells >= (sphere_only ? 50 : 44) && hi_cells <= 60 && !g.heating;
     if ((variant == 3 || (variant == 0 && auto_octant)) && symmetric && !coldens_grid) {
         std::string err;
         plan = get_plan(N, R, dr, sphere_only, true, 1, err);

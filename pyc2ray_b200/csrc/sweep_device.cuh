@@ -176,6 +176,12 @@ __device__ __forceinline__ double interp_weighted(double c1, double c2, double c
     return cdensi;
 }
 
+// Thick levels (mirror-image sweep): when every optical depth of the previous level is >= 0.6 -- a level-uniform fact carried
+// through the level barrier --, max(0.6, tau) of raytracing.cu:33 is tau itself, c_i w_i = s_i prod(c) and sum s_i = 1, so the
+// weighted mean collapses to prod(c) / sum_i s_i prod_{j != i} c_j: no selects, no numerator (sweep_octant.cu: entry_images).
+// 0.6 = 0x3FE3333333333333: a high word above 0x3FE33333 means tau > 0.6 (positive doubles order like integers)
+__device__ __forceinline__ bool tau_is_thick(double tau) { return __double2hiint(tau) > 0x3FE33333; }
+
 template <bool MASK, bool DIAG>
 __device__ __forceinline__ double interp_coldens(double c1, double c2, double c3, double c4, double wA,
                                                  double wB, unsigned flags)

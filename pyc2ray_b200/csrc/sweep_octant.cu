@@ -118,12 +118,15 @@ __device__ __forceinline__ void rate_cells(double (&tin)[NB], double (&tout)[NB]
 //            bits); every result is stored for the image across that plane as well
 //   BATCH:   images evaluated side by side, NIMG / BATCH rounds: the straight-line code of a round keeps ~30 registers
 //            per image live, so the batch is what fits the register budget of the launch shape
-template <int NIMG, int BATCH, int OPT, bool CLASS_B, int REP, bool DIAG, bool TEX, bool HEAT, bool DET>
+//   THK:     every optical depth of the previous level is >= 0.6 (level-uniform, octant_level), so max(0.6, tau) of
+//            raytracing.cu:33 is tau itself and the weighted mean collapses to prod(tau) / sum_i s_i prod_{j != i} tau_j
+//   ok:      cleared when an optical depth below 0.6 is stored (feeds the next level's THK decision)
+template <int NIMG, int BATCH, int OPT, bool CLASS_B, int REP, bool DIAG, bool TEX, bool HEAT, bool DET, bool THK>
 __device__ __forceinline__ void entry_images(const int4 ra, const int4 rb, double md, double inv_m, int slot, int lmax,
                                              int obase /* first local octant of this thread */, int gbase /* the same, global */,
                                              const unsigned (&X)[2], const unsigned (&Y)[2], const unsigned (&Z)[2],
                                              double* __restrict__ cur, const double* __restrict__ prev, double sk,
-                                             const SweepParams& p, const double2* __restrict__ log2_tab)
+                                             const SweepParams& p, const double2* __restrict__ log2_tab, bool& ok)
 {
     const double path = __hiloint2double(ra.y, ra.x);
     const double skn = sk * __hiloint2double(ra.w, ra.z);  // strength * kpref / (n path)
@@ -176,22 +179,36 @@ __device__ __forceinline__ void entry_images(const int4 ra, const int4 rb, doubl
             const double ntau = __ldg(p.nhi + pos[v]);
             const double* pv = prev + (obase + t) * lmax;
             const double c1 = pv[nb1], c2 = pv[nb2], c3 = pv[nb3], c4 = pv[nb4];
-            // interp_weighted (sweep_device.cuh) without its overflow branch, which is taken for the whole round below
-            const double m1 = dmax(c1, 0.6), m2 = dmax(c2, 0.6), m3 = dmax(c3, 0.6), m4 = dmax(c4, 0.6);
-            const double m12 = m1 * m2, m34 = m3 * m4;
-            const double w1 = s1 * (m2 * m34), w2 = s2 * (m1 * m34), w3 = s3 * (m4 * m12), w4 = s4 * (m3 * m12);
-            const double den = (w1 + w2) + (w3 + w4);
-            overflow |= !(den < 1e300);
-            double cin = (fma(c1, w1, c2 * w2) + fma(c3, w3, c4 * w4)) * fast_rcp(den);
-            if (DIAG) cin *= diag;
+            double cin;
+            if (THK) {
+                // all four >= 0.6 (zero-weight corners read the zero slot, kept at 1): c_i w_i = s_i prod(c), sum s_i = 1
+                const double m12 = c1 * c2, m34 = c3 * c4;
+                const double den = fma(m12, fma(s4, c3, s3 * c4), m34 * fma(s2, c1, s1 * c2));
+                overflow |= !(den < 1e300);
+                cin = (m12 * m34) * fast_rcp(den);
+            } else {
+                // interp_weighted (sweep_device.cuh) without its overflow branch, which is taken for the whole round below
+                const double m1 = dmax(c1, 0.6), m2 = dmax(c2, 0.6), m3 = dmax(c3, 0.6), m4 = dmax(c4, 0.6);
+                const double m12 = m1 * m2, m34 = m3 * m4;
+                const double w1 = s1 * (m2 * m34), w2 = s2 * (m1 * m34), w3 = s3 * (m4 * m12), w4 = s4 * (m3 * m12);
+                const double den = (w1 + w2) + (w3 + w4);
+                overflow |= !(den < 1e300);
+                cin = (fma(c1, w1, c2 * w2) + fma(c3, w3, c4 * w4)) * fast_rcp(den);
+            }
+            if (DIAG) {
+                cin *= diag;
+                if (flags & PC_SOURCE) cin = 0.0;  // the source cell "interpolates" the zero slot, which need not hold 0
+            }
             tin[v] = cin;
             tout[v] = fma(ntau, path, cin);
+            ok = ok && tau_is_thick(tout[v]);
         }
         if (__builtin_expect(overflow, 0)) {  // optical depths beyond 1e90: the reference's literal form (interp_weighted)
 #pragma unroll
             for (int u = 0; u < NB; u++) {
                 const double* pv = prev + (obase + tt[u]) * lmax;
                 tin[u] = interp_weighted<DIAG>(pv[nb1], pv[nb2], pv[nb3], pv[nb4], s1, s2, s3, s4, flags);
+                if (DIAG && (flags & PC_SOURCE)) tin[u] = 0.0;
                 tout[u] = fma(__ldg(p.nhi + pos[u]), path, tin[u]);
             }
         }
@@ -220,11 +237,11 @@ __device__ __forceinline__ void entry_images(const int4 ra, const int4 rb, doubl
     }  // rounds
 }
 
-template <int BLOCK, int NOCT, int OPT, int BATCH, int REP, bool DIAG, bool TEX, bool HEAT, bool ZF, bool PF, bool DET>
+template <int BLOCK, int NOCT, int OPT, int BATCH, int REP, bool DIAG, bool TEX, bool HEAT, bool ZF, bool PF, bool DET, bool THK>
 __device__ __forceinline__ void octant_level(const int4* __restrict__ plan, int ncells, int beg, int mid, int end, double md,
                                              double inv_m, double* __restrict__ cur, const double* __restrict__ prev, int lmax,
                                              const unsigned* __restrict__ wrap_tab, int hi, int part, double sk,
-                                             const SweepParams& p, const double2* __restrict__ log2_tab)
+                                             const SweepParams& p, const double2* __restrict__ log2_tab, bool& ok)
 {
     constexpr int G = NOCT / OPT;                 // warps that share an entry
     static_assert((BLOCK / 32) % G == 0 && BLOCK % 32 == 0, "the warps of a CTA must divide evenly over the image groups");
@@ -278,11 +295,12 @@ __device__ __forceinline__ void octant_level(const int4* __restrict__ plan, int 
             Z[0] = Z[1] = w[2 * side + (fz ? hi - dk : hi + dk)];
         }
         if (OPT < 2 || e < mid)
-            entry_images<OPT, BATCH, OPT, false, REP, DIAG, TEX, HEAT, DET>(ra, rb, md, inv_m, e - beg, lmax, obase, gbase, X, Y, Z, cur, prev, sk,
-                                                                        p, log2_tab);
+            entry_images<OPT, BATCH, OPT, false, REP, DIAG, TEX, HEAT, DET, THK>(ra, rb, md, inv_m, e - beg, lmax, obase, gbase, X, Y, Z, cur,
+                                                                             prev, sk, p, log2_tab, ok);
         else
-            entry_images<(OPT >= 2 ? OPT / 2 : 1), BATCH, OPT, true, REP, DIAG, TEX, HEAT, DET>(ra, rb, md, inv_m, e - beg, lmax, obase, gbase, X,
-                                                                                           Y, Z, cur, prev, sk, p, log2_tab);
+            entry_images<(OPT >= 2 ? OPT / 2 : 1), BATCH, OPT, true, REP, DIAG, TEX, HEAT, DET, THK>(ra, rb, md, inv_m, e - beg, lmax, obase,
+                                                                                                gbase, X, Y, Z, cur, prev, sk, p,
+                                                                                                log2_tab, ok);
     }
 }
 
@@ -318,7 +336,9 @@ sweep_octant_kernel(const int4* __restrict__ plan, int ncells, const int* __rest
     for (int t = threadIdx.x; t < 256 * REP; t += BLOCK) log2_all[t] = __ldg(p.log2_tab + t / REP);
     const double2* log2_tab = log2_all + (REP > 1 ? (threadIdx.x & (REP - 1)) : 0);
     // the zero slot (last of every level buffer, sweep_plan.cu: resolve_zero_slot): zero-weight corners and the source cell
-    if (threadIdx.x < 2 * NOCT) sh_cd[(size_t)(threadIdx.x + 1) * lmax - 1] = 0.0;
+    // Its value only ever meets an exact zero weight.  1 (not 0) lets the thick-level form of the interpolation multiply it in
+    // without a max(0.6, .); the deterministic instantiations keep the 0 all sweep variants share (bit-identical sums).
+    if (threadIdx.x < 2 * NOCT) sh_cd[(size_t)(threadIdx.x + 1) * lmax - 1] = DET ? 0.0 : 1.0;
     const int i0 = p.src_pos[3 * ns + 0], j0 = p.src_pos[3 * ns + 1], k0 = p.src_pos[3 * ns + 2];
     const double sk = p.src_flux[ns] * p.kpref;
     for (int t = threadIdx.x; t < 3 * side; t += BLOCK) {
@@ -333,19 +353,25 @@ sweep_octant_kernel(const int4* __restrict__ plan, int ncells, const int* __rest
     __syncthreads();
 
     int beg = level_start[0], end = level_start[1];
+    bool prev_thick = false;
     for (int m = 0; m < nlevels; m++) {
         const int next_end = level_start[min(m + 2, nlevels)];
         const int mid = level_mid[m];
         double* cur = sh_cd + (size_t)(m & 1) * NOCT * lmax;
         const double* prev = sh_cd + (size_t)((m & 1) ^ 1) * NOCT * lmax;
         const double md = (double)m, inv_m = inv_level[m];
+        bool ok = true;
         if (m < 2)  // the source cell and its 26 neighbours: the only cells with diagonal factors (raytracing.cu:431-441)
-            octant_level<BLOCK, NOCT, OPT, BATCH, REP, true, TEX, HEAT, ZF, PF, DET>(plan, ncells, beg, mid, end, md, inv_m, cur, prev, lmax,
-                                                                                wrap_tab, hi, part, sk, p, log2_tab);
+            octant_level<BLOCK, NOCT, OPT, BATCH, REP, true, TEX, HEAT, ZF, PF, DET, false>(plan, ncells, beg, mid, end, md, inv_m, cur, prev,
+                                                                                       lmax, wrap_tab, hi, part, sk, p, log2_tab, ok);
+        else if (!DET && prev_thick)
+            octant_level<BLOCK, NOCT, OPT, BATCH, REP, false, TEX, HEAT, ZF, PF, DET, !DET>(plan, ncells, beg, mid, end, md, inv_m, cur, prev,
+                                                                                       lmax, wrap_tab, hi, part, sk, p, log2_tab, ok);
         else
-            octant_level<BLOCK, NOCT, OPT, BATCH, REP, false, TEX, HEAT, ZF, PF, DET>(plan, ncells, beg, mid, end, md, inv_m, cur, prev, lmax,
-                                                                                 wrap_tab, hi, part, sk, p, log2_tab);
-        __syncthreads();
+            octant_level<BLOCK, NOCT, OPT, BATCH, REP, false, TEX, HEAT, ZF, PF, DET, false>(plan, ncells, beg, mid, end, md, inv_m, cur, prev,
+                                                                                        lmax, wrap_tab, hi, part, sk, p, log2_tab, ok);
+        // level barrier; it also tells every thread whether all optical depths of this level reached 0.6
+        prev_thick = __syncthreads_and(ok) != 0;
         beg = end;
         end = next_end;
     }
