@@ -50,8 +50,8 @@ __device__ __forceinline__ double fast_log2(int hi, int lo, const double2* __res
     const double2 t = tab[((hi >> 12) & 0xff) * REP];
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
     const double r = fma(m, t.x, -1.0);  // |r| <= 2^-9
-    double p = fma(r, kLog2Poly[5], kLog2Poly[4]);
-    p = fma(r, p, kLog2Poly[3]);
+    // (the r^6 term, |K[5] r^6| <= 1.3e-17, is below the rounding of the result and left out)
+    double p = fma(r, kLog2Poly[4], kLog2Poly[3]);
     p = fma(r, p, kLog2Poly[2]);
     p = fma(r, p, kLog2Poly[1]);
     p = fma(r, p, kLog2Poly[0]);

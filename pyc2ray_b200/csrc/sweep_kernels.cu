@@ -22,7 +22,7 @@
 //   * strength/Vfact (rates.cu:24) is a product with the plan's 1/(n path); phi/nHI (raytracing.cu:324) is the
 //     same for every source and is applied once per cell after the sweep (finish_phi_kernel);
 //   * log10(tau) -> table index (rates.cu:77-78) is index = a + b*log2(tau) with log2 from a
-//     256-entry mantissa table in shared memory and a degree-6 polynomial (|error| < 2 ulp);
+//     256-entry mantissa table in shared memory and a degree-5 polynomial (|error| < 2 ulp);
 //   * T[i0] + r*(T[i1]-T[i0]) reads one 16-byte {T[i], T[i+1]-T[i]} pair (through the texture pipe);
 //   * int <-> double conversions by 2^52-offset additions (fp64 pipe) instead of I2F / F2I (XU pipe).
 // Results agree with the reference's own expression order to ~1e-13 relative (tests/).
