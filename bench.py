@@ -740,7 +740,7 @@ def main():
             from pyc2ray_b200.parallel import slab_edges, SlabHalo
             edges, hh = slab_edges(pos0[0::3], N, world, R)
             if edges is not None:
-                halo = SlabHalo(edges, hh, N, rank, world)
+                halo = SlabHalo(edges, hh, N, rank, world, peer=os.environ.get("ASORA_PEER_HALO", "1") != "0")
                 o, cnt = halo.own_cells()
                 want = phi_t[o:o + cnt].clone()          # the all-reduced rates of the list-order run, my planes
                 mine = (pos0[0::3] >= halo.lo) & (pos0[0::3] < halo.hi)
@@ -765,6 +765,8 @@ def main():
                         ts = min(ts or 1e30, el)
                 torch.cuda.synchronize()
                 check(L.asora_set_active_slab(0, 0))
+                peer_mode = halo.peer
+                halo.close()
                 got = phi_t[o:o + cnt]
                 scale = float(want.abs().max().item())
                 rel = ((got - want).abs() / torch.clamp(want.abs(), min=1e-12 * scale)).max().reshape(1)
@@ -772,9 +774,11 @@ def main():
                 counts = torch.tensor([float(nmine)], device="cuda")
                 dist.all_reduce(counts, op=dist.ReduceOp.MAX)
                 slab = {"ms": ts, "halo_planes": hh, "max_sources_per_rank": int(counts.item()),
+                        "halo_exchange": "neighbours' halo planes read over NVLink from their GPUs' memory (CUDA IPC), one kernel per "
+                                         "neighbour" if peer_mode else "NCCL send/recv",
                         "max_rel_vs_allreduce": float(rel.item()),
                         "what": "sources sharded by x-plane ranges of equal source counts, sweep + two halo reductions of "
-                                f"{hh} planes ({hh * N * N * 8 / 1e6:.0f} MB each) with the neighbouring ranks; every rank ends with "
+                                f"{hh} planes ({hh * N * N * 8 / 1e6:.0f} MB each) from the neighbouring ranks; every rank ends with "
                                 "the complete rates of its own planes (the input of its share of the chemistry)"}
                 if slab["max_rel_vs_allreduce"] > 1e-10:
                     failures.append("strong.fixed_256.slab")

@@ -146,6 +146,19 @@ int asora_buffer_upload_range(int which, const double* host, int64_t cell_offset
 /* Device -> device copy between two named buffers (N^3 doubles), on the context's stream. */
 int asora_buffer_copy(int dst, int src);
 
+/* Peer-memory halo exchange of slab-decomposed multi-GPU runs (one process per GPU on one node; replaces the N^3 Reduce + Bcast
+ * of evolve.py:433-437,480-497 together with asora_set_active_slab).  ipc_export writes the 64-byte CUDA IPC handle of grid
+ * buffer `which`; a neighbouring rank passes it to ipc_open and gets a device pointer to that buffer on the exporting GPU
+ * (valid until ipc_close or the exporter's device_close).  peer_halo then does, on this context's stream,
+ *   buffer[which][cell_offset .. +cell_count) += peer_buf[cell_offset .. +cell_count)   (add != 0: rates a neighbour computed)
+ *   buffer[which][cell_offset .. +cell_count)  = peer_buf[...]                          (add == 0: a neighbour's new xh_av)
+ * reading the neighbour's memory over NVLink.  Ordering across ranks (the neighbour has finished writing, nobody overwrites what
+ * is still being read) is the caller's: pyc2ray_b200.parallel.SlabHalo brackets the calls with the collectives of its loop. */
+int asora_ipc_export(int which, unsigned char* handle64);
+int asora_ipc_open(const unsigned char* handle64, void** dev_ptr);
+int asora_ipc_close(void* dev_ptr);
+int asora_peer_halo(int which, const void* peer_buf, int64_t cell_offset, int64_t cell_count, int add);
+
 /* Ray-trace sources [src_begin, src_begin+src_count) of the uploaded list using the device-resident
  * NDENS and XH_AV buffers; rates are accumulated into PHI_ION, which is zeroed first when
  * zero_phi != 0.  Asynchronous on the context's stream; asora_sync() waits. */

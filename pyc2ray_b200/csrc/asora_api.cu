@@ -1192,6 +1192,52 @@ int asora_buffer_copy(int dst, int src)
     return 0;
 }
 
+// ---- peer-memory halo exchange (slab-decomposed multi-GPU runs) ------------------------------------------------------
+// A rank exports its grid buffers by CUDA IPC; its neighbours map them and read the halo planes straight over NVLink
+// from a kernel, instead of four NCCL send/recv pairs per exchange.
+int asora_ipc_export(int which, unsigned char* handle64)
+{
+    if (int rc = need_init()) return rc;
+    if (!handle64) return fail("ipc_export: null handle buffer");
+    if (int rc = ensure_buffer(which)) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, g.buf[which]));
+    std::memcpy(handle64, &h, sizeof(h));
+    return 0;
+}
+
+int asora_ipc_open(const unsigned char* handle64, void** dev_ptr)
+{
+    if (int rc = need_init()) return rc;
+    if (!handle64 || !dev_ptr) return fail("ipc_open: null argument");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, sizeof(h));
+    CK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int asora_ipc_close(void* dev_ptr)
+{
+    if (!dev_ptr) return 0;
+    CK(cudaIpcCloseMemHandle(dev_ptr));
+    return 0;
+}
+
+int asora_peer_halo(int which, const void* peer_buf, int64_t cell_offset, int64_t cell_count, int add)
+{
+    Range range(add ? "asora:peer_halo_add" : "asora:peer_halo_copy");
+    if (int rc = need_init()) return rc;
+    if (int rc = ensure_buffer(which)) return rc;
+    if (!peer_buf) return fail("peer_halo: null peer buffer");
+    if (cell_offset < 0 || cell_count < 0 || cell_offset + cell_count > g.ncell) return fail("peer_halo: range outside the grid");
+    if (which == ASORA_BUF_TEMP) g.chem_factors_valid = false;
+    cudaError_t e = launch_peer_halo(g.buf[which] + cell_offset, static_cast<const double*>(peer_buf) + cell_offset, cell_count,
+                                     add != 0, g.stream);
+    if (e != cudaSuccess) return fail_cuda("peer_halo_kernel launch", e);
+    return 0;
+}
+
 int asora_global_pass_device(double dt, double bh00, double albpow, double colh0, double temph0, double abu_c,
                              int* conv_flag, double* sum_xh1, double* sum_xh0)
 {

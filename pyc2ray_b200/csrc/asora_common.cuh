@@ -165,6 +165,7 @@ cudaError_t launch_sweep_grid(const SweepParams& p, int ngroups, unsigned* count
 
 cudaError_t launch_prepare_nhi(const double* ndens, const double* xh_av, double* ntau, double sig_dr, int64_t ncell,
                                cudaStream_t stream);
+cudaError_t launch_peer_halo(double* dst, const double* src, int64_t n, bool add, cudaStream_t stream);
 cudaError_t launch_finish_phi(double* phi, const double* ntau, const double* keep, int64_t ncell, cudaStream_t stream);
 cudaError_t launch_prepare_nhi_transposed(const double* ndens, const double* xh_av, double* ntau, double* ntau_t, double sig_dr,
                                           int N, cudaStream_t stream);

@@ -725,3 +725,41 @@ cudaError_t launch_reverse_axes(const double* in, double* out, int N, cudaStream
     reverse_axes_kernel<<<grid, block, 0, stream>>>(in, out, N);
     return cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------------------------------
+// halo exchange of a slab-decomposed run over peer memory (NVLink): dst[i] (+)= src[i], src being the same buffer of a
+// neighbouring rank's GPU, mapped into this process by CUDA IPC (asora_ipc_open).  16-byte accesses when both are aligned.
+// ---------------------------------------------------------------------------------------------------
+template <bool ADD>
+__global__ void peer_halo_kernel(double* __restrict__ dst, const double* __restrict__ src, int64_t n)
+{
+    const int64_t n2 = n >> 1;
+    double2* d2 = reinterpret_cast<double2*>(dst);
+    const double2* s2 = reinterpret_cast<const double2*>(src);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+        const double2 v = s2[i];
+        if (ADD) {
+            double2 o = d2[i];
+            o.x += v.x;
+            o.y += v.y;
+            d2[i] = o;
+        } else {
+            d2[i] = v;
+        }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) dst[n - 1] = ADD ? dst[n - 1] + src[n - 1] : src[n - 1];
+}
+
+cudaError_t launch_peer_halo(double* dst, const double* src, int64_t n, bool add, cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    if ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) return cudaErrorMisalignedAddress;
+    int64_t blocks = (n / 2 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    if (add)
+        peer_halo_kernel<true><<<(int)blocks, 256, 0, stream>>>(dst, src, n);
+    else
+        peer_halo_kernel<false><<<(int)blocks, 256, 0, stream>>>(dst, src, n);
+    return cudaGetLastError();
+}

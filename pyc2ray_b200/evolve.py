@@ -7,6 +7,7 @@ copies).  Here ndens, temp, xh, xh_av, xh_intermed and phi_ion stay in HBM for t
 loop; per iteration the host sees three scalars (conv_flag, sum x, sum 1-x).
 """
 import ctypes
+import os
 import time
 
 import numpy as np
@@ -65,7 +66,8 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
             if edges is None and decomposition == "slab":
                 raise ValueError("slab decomposition impossible: a halo does not fit the neighbouring slab")
         if edges is not None:
-            halo = SlabHalo(edges, h, N, rank, nprocs, group)
+            # halo planes read straight from the neighbours' GPUs over NVLink (CUDA IPC); ASORA_PEER_HALO=0: NCCL send/recv
+            halo = SlabHalo(edges, h, N, rank, nprocs, group, peer=os.environ.get("ASORA_PEER_HALO", "1") != "0")
             x0 = np.mod(np.asarray(src_pos)[0].astype(np.int64) - 1, N)
             mine = (x0 >= halo.lo) & (x0 < halo.hi)
             srcpos_flat, normflux_flat = format_sources(np.asarray(src_pos)[:, mine], np.asarray(src_flux)[mine])
@@ -178,7 +180,7 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
                 tch0p = time.perf_counter()
                 scal.copy_(torch.tensor([flag.value, s1.value, s0.value], dtype=torch.float64))
                 allreduce_sum_(scal, group)   # conv_flag, sum x, sum 1-x over all planes
-                halo.gather_xh_(xav_t)        # my neighbours' new xh_av inside my ray-tracing reach
+                halo.gather_xh_(xav_t, synced=True)   # my neighbours' new xh_av inside my ray-tracing reach
                 torch.cuda.synchronize()
                 g = scal.tolist()
                 conv_flag, sum_xh1_int, sum_xh0_int = int(round(g[0])), g[1], g[2]
@@ -217,6 +219,8 @@ def _evolve_device(dt, dr, src_flux, src_pos, temp, ndens, xh, photo_thin_table,
     finally:
         L.asora_set_sphere_only(0)
         L.asora_set_active_slab(0, 0)
+        if halo is not None:
+            halo.close()   # unmap the neighbours' buffers (no collective: safe on the error path too)
     evolve3D.last_loop_seconds = time.perf_counter() - t_loop0  # the convergence loop alone: no host<->device grid copies
     evolve3D.last_phase_seconds = phases
     if rsag:

@@ -40,6 +40,10 @@ SIGNATURES = {
     "asora_buffer_upload_range": (_i, [_i, c_dp, _i64, _i64]),
     "asora_buffer_download": (_i, [_i, c_dp]),
     "asora_buffer_copy": (_i, [_i, _i]),
+    "asora_ipc_export": (_i, [_i, ctypes.c_char_p]),
+    "asora_ipc_open": (_i, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "asora_ipc_close": (_i, [ctypes.c_void_p]),
+    "asora_peer_halo": (_i, [_i, ctypes.c_void_p, _i64, _i64, _i]),
     "asora_raytrace_device": (_i, [_d, _d, _d, _i, _i, _d, _d, _i, _i]),
     "asora_global_pass_device": (_i, [_d, _d, _d, _d, _d, _d, ctypes.POINTER(_i), c_dp, c_dp]),
     "asora_set_active_slab": (_i, [_i, _i]),

@@ -107,15 +107,102 @@ def slab_edges(src_x0, N, nprocs, R):
 
 class SlabHalo:
     """Halo exchanges of one rank in a slab-decomposed run; works on flat torch tensors of N^3 doubles (CUDA ->
-    NCCL send/recv, CPU -> gloo)."""
+    NCCL send/recv, CPU -> gloo).
 
-    def __init__(self, edges, h, N, rank, nprocs, group=None):
+    ``peer=True`` (CUDA ranks of one node, on the context's own PHI_ION / XH_AV buffers): the neighbours' buffers are
+    mapped by CUDA IPC once (asora_ipc_export / asora_ipc_open) and the halo planes are read straight over NVLink by one
+    kernel per neighbour (asora_peer_halo) instead of four NCCL send/recv pairs plus staging copies per exchange.  The
+    cross-rank ordering comes from collectives on the same stream: a one-element all-reduce before the rates are read
+    (every rank's sweep has finished), and the caller's own collective between the two exchanges of an iteration (the
+    3-scalar all-reduce of the evolve loop: every rank has finished reading before anybody's next sweep overwrites)."""
+
+    def __init__(self, edges, h, N, rank, nprocs, group=None, peer=False):
         self.N, self.h, self.rank, self.nprocs, self.group = N, h, rank, nprocs, group
         self.lo, self.hi = edges[rank], edges[rank + 1]
         self.left, self.right = (rank - 1) % nprocs, (rank + 1) % nprocs
         self.plane = N * N
         self._tmp = None
+        self._peer = None
+        if peer:
+            self._open_peers()
 
+    # -- peer-memory mode -----------------------------------------------------------------------------------------
+    def _open_peers(self):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from .lib import _cabi
+        L, check = _cabi.L, _cabi.check
+        bufs = (_cabi.BUF_PHI_ION, _cabi.BUF_XH_AV)
+        mine = torch.zeros(len(bufs) * 64, dtype=torch.uint8)
+        for i, b in enumerate(bufs):
+            raw = ctypes.create_string_buffer(64)
+            check(L.asora_ipc_export(b, raw))
+            mine[64 * i:64 * (i + 1)] = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8)
+        mine = mine.cuda()
+        allh = [torch.empty_like(mine) for _ in range(self.nprocs)]
+        dist.all_gather(allh, mine, group=self.group)
+        ptrs = {}
+        try:
+            for nb in {self.left, self.right}:
+                hb = allh[nb].cpu().numpy().tobytes()
+                ptrs[nb] = {}
+                for i, b in enumerate(bufs):
+                    p = ctypes.c_void_p()
+                    check(L.asora_ipc_open(hb[64 * i:64 * (i + 1)], ctypes.byref(p)))
+                    ptrs[nb][b] = p
+        except RuntimeError as e:
+            import warnings
+            warnings.warn(f"SlabHalo: peer access to the neighbours' buffers failed ({e}); using NCCL send/recv")
+            for d in ptrs.values():
+                for p in d.values():
+                    L.asora_ipc_close(p)
+            ptrs = None
+        # all ranks use the same mode: peer access must have worked everywhere
+        ok = torch.tensor([1.0 if ptrs is not None else 0.0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if ok.item() < 1.0:
+            if ptrs is not None:
+                for d in ptrs.values():
+                    for p in d.values():
+                        L.asora_ipc_close(p)
+            ptrs = None
+        self._peer = ptrs
+        self._token = torch.zeros(1, device="cuda")
+
+    @property
+    def peer(self):
+        return self._peer is not None
+
+    def close(self):
+        """Unmap the neighbours' buffers.  Not a collective; the owners free their buffers only at device_close, after the
+        collectives that end a time step."""
+        if self._peer is not None:
+            from .lib import _cabi
+            _cabi.L.asora_sync()
+            for d in self._peer.values():
+                for p in d.values():
+                    _cabi.L.asora_ipc_close(p)
+            self._peer = None
+
+    def _rank_barrier(self):
+        """Every rank has reached this point (and, having synchronised its sweep / chemistry before, finished that work)."""
+        import torch
+        import torch.distributed as dist
+        dist.all_reduce(self._token, group=self.group)
+        torch.cuda.current_stream().synchronize()
+
+    def _peer_done(self):
+        from .lib import _cabi
+        _cabi.check(_cabi.L.asora_sync())   # my reads of the neighbours' memory are complete before I enter the next collective
+
+    def _peer_halo(self, buf, nb, first_plane, add):
+        from .lib import _cabi
+        first_plane %= self.N
+        assert first_plane + self.h <= self.N, "halo straddles the periodic boundary"
+        _cabi.check(_cabi.L.asora_peer_halo(buf, self._peer[nb][buf], first_plane * self.plane, self.h * self.plane, int(add)))
+
+    # -- geometry -------------------------------------------------------------------------------------------------
     def _planes(self, t, start, count):
         start %= self.N
         assert start + count <= self.N, "halo straddles the periodic boundary"
@@ -138,9 +225,18 @@ class SlabHalo:
             req.wait()
 
     def reduce_phi_(self, phi):
-        """Add to this rank's own planes the rates its neighbours computed for them (in place)."""
+        """Add to this rank's own planes the rates its neighbours computed for them (in place).  Peer mode: ``phi`` must be
+        the context's PHI_ION buffer."""
         import torch
         h, n = self.h, self.h * self.plane
+        if self._peer is not None:
+            from .lib import _cabi
+            _cabi.check(_cabi.L.asora_sync())                                      # my sweep has finished ...
+            self._rank_barrier()                                                   # ... and so has everybody's
+            self._peer_halo(_cabi.BUF_PHI_ION, self.right, self.hi - h, True)      # the right neighbour's left halo = my last h planes
+            self._peer_halo(_cabi.BUF_PHI_ION, self.left, self.lo, True)           # the left neighbour's right halo = my first h planes
+            self._peer_done()
+            return phi
         if self._tmp is None or self._tmp.device != phi.device:
             self._tmp = torch.empty(2 * n, dtype=phi.dtype, device=phi.device)
         from_right, from_left = self._tmp[:n], self._tmp[n:]
@@ -149,9 +245,22 @@ class SlabHalo:
         self._planes(phi, self.lo, h).add_(from_left)        # the left neighbour's right halo = my first h planes
         return phi
 
-    def gather_xh_(self, xh_av):
-        """Refresh the halo planes of xh_av from the neighbours that own them (in place)."""
+    def gather_xh_(self, xh_av, synced=False):
+        """Refresh the halo planes of xh_av from the neighbours that own them (in place).  Peer mode: ``xh_av`` must be the
+        context's XH_AV buffer; ``synced``: a collective on this stream already followed every rank's chemistry pass."""
         h = self.h
+        if self._peer is not None:
+            from .lib import _cabi
+            import torch
+            if synced:
+                torch.cuda.current_stream().synchronize()   # the caller's collective has completed here
+            else:
+                _cabi.check(_cabi.L.asora_sync())
+                self._rank_barrier()
+            self._peer_halo(_cabi.BUF_XH_AV, self.right, self.hi, False)
+            self._peer_halo(_cabi.BUF_XH_AV, self.left, self.lo - h, False)
+            self._peer_done()
+            return xh_av
         self._exchange(self._planes(xh_av, self.lo, h).contiguous(), self._planes(xh_av, self.hi - h, h).contiguous(),
                        self._planes(xh_av, self.hi, h), self._planes(xh_av, self.lo - h, h))
         return xh_av
