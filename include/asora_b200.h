@@ -235,7 +235,7 @@ int asora_set_deterministic(int on);
 int asora_set_grey_notables(int on);
 
 /* Override the launch shape of the shared-memory sweep: sources per CTA (1 or 2) and, in the low 16 bits of
- * block_threads, threads per CTA (256, 512, 768, 896 or 1024 for one source; 256, 512 or 1024 for two); 0 =
+ * block_threads, threads per CTA (256, 512, 768, 896 or 1024 for one source; 256 for two); 0 =
  * automatic.  Bits 16-18 of block_threads toggle launch options against their automatic choice (copies of the
  * log2 table in shared memory, table gathers through the texture pipe, offsets word fetched one cell ahead);
  * bit 19 toggles the (k,i,j)-ordered grid copies for z-face cells (automatic only for sweeps of >= 5e8 updates);

@@ -294,8 +294,6 @@ cudaError_t launch_sweep_smem(const SweepPlan& plan, const SweepParams& p, int S
     ASORA_CASE(2, 256, 3)  // 80 registers: at 64 the two-source body spills and its speed depends on where
     ASORA_CASE(1, 768, 1)
     ASORA_CASE(1, 896, 1)
-    ASORA_CASE(2, 512, 2)
-    ASORA_CASE(2, 1024, 1)
 #undef ASORA_CASE
     return cudaErrorInvalidValue;
 }
