@@ -428,7 +428,15 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
     // R = 30 14.5 vs 17.0 ms, R = 34 20.2 vs 26.8 ms (10^4 sources); sphere only from q_max = 50: R = 30 11.1 vs 11.5 ms,
     // R = 34 15.5 vs 16.6 ms, but R = 25 7.3 vs 7.0 ms.  Smaller radii and larger ones (split sweeps) stay on variant 1
     // (R = 20: 52.1 vs 54.0 ms for 10^5 sources; R = 40: 10.7 vs 11.6 ms).
-    const bool auto_octant = hi_cells >= (sphere_only ? 50 : 44) && hi_cells <= 60 && !g.heating;
+    bool auto_octant = hi_cells >= (sphere_only ? 50 : 44) && hi_cells <= (sphere_only ? 60 : 126) && !g.heating;
+    if (auto_octant && variant == 0 && hi_cells > 60) {
+        // quadrant CTAs, two per SM: decided from a cell count, before an octant plan that would not be used is built
+        const size_t cells = (size_t)sweep_plan_octant_level_cells(N, R, dr, false);
+        const size_t side_o = 2 * (size_t)hi_cells + 1, nl = (size_t)hi_cells + 1;
+        const size_t smem2 = 256 * sizeof(double2) + 4 * cells * sizeof(double) + nl * sizeof(double) + 6 * side_o * sizeof(unsigned) +
+                             (2 * nl + 1) * sizeof(int);
+        if (2 * smem2 + 2048 > (size_t)g.smem_per_sm) auto_octant = false;
+    }
     if ((variant == 3 || (variant == 0 && auto_octant)) && symmetric && !coldens_grid) {
         std::string err;
         plan = get_plan(N, R, dr, sphere_only, true, 1, err);
@@ -441,7 +449,10 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
                 if (variant == 3) return fail("sweep variant 3 forced but a level does not fit in shared memory");
                 plan = nullptr;
             }
-            if (plan && variant == 0 && noct < 8) plan = nullptr;  // automatic: only while all eight octants fit one CTA
+            // automatic: while all eight octants fit one CTA, or -- full cell set -- two quadrant CTAs fit one SM (below)
+            if (plan && variant == 0 && noct < 8 &&
+                (sphere_only || sweep_octant_smem_bytes(*plan, 2, 1, true) * 2 + 2048 > (size_t)g.smem_per_sm))
+                plan = nullptr;
         }
         if (plan) {
             // Launch shape (measured on B200, scripts/octant_probe.py; DESIGN.md, "Mirror-image sweep").  Large levels:
@@ -451,6 +462,9 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
             const int maxc = plan->max_level_cells;
             int auto_opts = 0;
             if (g.oct_noct == 0 && maxc >= 512 && sweep_octant_smem_bytes(*plan, 4, 1, true) * 2 + 2048 <= (size_t)g.smem_per_sm) noct = 4;
+            // beyond that (q_max 61 ... ~84 at 256^3): quadrants, two CTAs per SM (R = 38: 7.6 vs 9.0 ms with variant 1 for 2000
+            // sources, R = 44: 11.8 vs 13.7 ms; half-spaces with one CTA per SM: 8.4 / 13.7 ms)
+            else if (g.oct_noct == 0 && variant == 0 && noct < 8) noct = 2;
             if (noct == 8) {
                 if (maxc >= 512) { opt = 4; batch = 2; block = 512; }
                 else if (maxc >= 128) { opt = 4; batch = 2; block = 128; }
@@ -459,8 +473,8 @@ int run_sweep(double R, double sig, double dr, int begin, int count, double minl
                 opt = 4; batch = 4; block = 256;
                 auto_opts = 4 | 8;
             } else {
-                opt = 2; batch = 2; block = 192;
-                auto_opts = 8;
+                opt = 2; batch = 2; block = variant == 0 ? 256 : 192;
+                auto_opts = variant == 0 ? (4 | 8) : 8;
             }
             if (g.oct_opt > 0) opt = g.oct_opt;
             if (g.oct_batch > 0) batch = g.oct_batch;

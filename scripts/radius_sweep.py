@@ -18,7 +18,7 @@ check(L.asora_buffer_upload(_cabi.BUF_XH_AV, _cabi.dptr(np.ascontiguousarray(xh.
 print("| R (cells) | sources | variant | levels | ms | us/source | G updates/s | ns per source and sphere cell (paper unit) |")
 print("|---|---|---|---|---|---|---|---|")
 for R, counts in ((5.0, (10000, 100000)), (10.0, (1, 100, 10000, 100000, 1000000)), (10.76, (100000,)), (20.0, (10000,)),
-                  (30.0, (1, 100, 1000, 10000, 100000)), (40.0, (2000,)), (50.0, (1000,)), (60.0, (500,)), (70.0, (300,)), (80.0, (128,)), (100.0, (64,)),
+                  (30.0, (1, 100, 1000, 10000, 100000)), (36.0, (4000,)), (40.0, (2000,)), (45.0, (2000,)), (48.0, (1000,)), (50.0, (1000,)), (60.0, (500,)), (70.0, (300,)), (80.0, (128,)), (100.0, (64,)),
                   (1e4, (1, 16, 64))):
     for ns in counts:
         srcpos = p.generate_test_sources(N, ns); flux = np.ones(ns)

@@ -177,3 +177,32 @@ def test_plan_cache_hits():
         _cabi.L.asora_set_tuning(0, 0)
         _cabi.L.asora_set_sphere_only(0)
         libasora.device_close()
+
+
+def test_octant_quadrants_automatic_at_r40():
+    """R = 40 on a 160^3 mesh (q_max = 70: half-spaces no longer fit two to an SM): the automatic selection takes the
+    mirror-image sweep with quadrants as CTAs; against the oracle and against variant 1."""
+    import ctypes
+    from pyc2ray_b200.lib import _cabi, libasora
+    from tests.fields import f1_fields, tables, SIG
+    from tests.test_gpu_parity import _setup, _sweep, _assert_close
+    from pyc2ray_b200.utils.sourceutils import format_sources, generate_test_sources
+    N, ns, R = 160, 3, 40.0
+    srcpos = generate_test_sources(N, ns, seed=40)
+    flux = 10 ** np.random.default_rng(40).normal(0, 0.5, size=ns)
+    ndens, xh = f1_fields(N, srcpos)
+    thin, thick, dlogtau, _ = tables("bb1e5")
+    pos_flat, flux_flat = format_sources(srcpos, flux)
+    c = dict(N=N, R=R, sig=SIG, dr=6e20, ndens=ndens, xh=xh, thin=thin, thick=thick, minlogtau=-20.0, dlogtau=dlogtau,
+             NumTau=thin.size, pos_flat=pos_flat, flux_flat=flux_flat)
+    ref, _, n = _oracle(c)
+    _setup(libasora, c)
+    try:
+        phi, used, upd = _sweep(libasora, _cabi, c, 0)
+        assert used == 3 and upd == n
+        v1, used1, _ = _sweep(libasora, _cabi, c, 1)
+        assert used1 == 1
+    finally:
+        libasora.device_close()
+    _assert_close(phi, ref, "R=40 automatic (quadrant CTAs) vs oracle")
+    _assert_close(phi, v1, "R=40 automatic (quadrant CTAs) vs variant 1", rtol=1e-11)
