@@ -740,7 +740,8 @@ def main():
             from pyc2ray_b200.parallel import slab_edges, SlabHalo
             edges, hh = slab_edges(pos0[0::3], N, world, R)
             if edges is not None:
-                halo = SlabHalo(edges, hh, N, rank, world, peer=os.environ.get("ASORA_PEER_HALO", "1") != "0")
+                halo = SlabHalo(edges, hh, N, rank, world, peer=os.environ.get("ASORA_PEER_HALO", "1") != "0",
+                                stream_ordered=True)   # asora_set_stream above: sweeps, collectives and halo kernels share a stream
                 o, cnt = halo.own_cells()
                 want = phi_t[o:o + cnt].clone()          # the all-reduced rates of the list-order run, my planes
                 mine = (pos0[0::3] >= halo.lo) & (pos0[0::3] < halo.hi)
@@ -749,7 +750,8 @@ def main():
                 libasora.source_data_to_device(pos_m, np.ascontiguousarray(flux0[mine]), nmine)
                 # planes this rank's sweeps can read: the full cell set reaches q_max planes beyond its sources (rates: hh)
                 reach = min(qmax.value, N // 2)
-                if (halo.hi - halo.lo) + 2 * reach < N:
+                # (only when that is well under the whole grid: a restricted sweep gives up the z-face grid copies)
+                if (halo.hi - halo.lo) + 2 * reach <= 0.6 * N:
                     check(L.asora_set_active_slab((halo.lo - reach) % N, (halo.hi - halo.lo) + 2 * reach))
                 ts = None
                 for rep in range(4):

@@ -116,8 +116,11 @@ class SlabHalo:
     (every rank's sweep has finished), and the caller's own collective between the two exchanges of an iteration (the
     3-scalar all-reduce of the evolve loop: every rank has finished reading before anybody's next sweep overwrites)."""
 
-    def __init__(self, edges, h, N, rank, nprocs, group=None, peer=False):
+    def __init__(self, edges, h, N, rank, nprocs, group=None, peer=False, stream_ordered=False):
         self.N, self.h, self.rank, self.nprocs, self.group = N, h, rank, nprocs, group
+        # peer mode: the context's stream is torch's current stream (asora_set_stream), so kernels and collectives are
+        # ordered by the stream and the host synchronisations between them can be left out
+        self.stream_ordered = stream_ordered
         self.lo, self.hi = edges[rank], edges[rank + 1]
         self.left, self.right = (rank - 1) % nprocs, (rank + 1) % nprocs
         self.plane = N * N
@@ -190,11 +193,13 @@ class SlabHalo:
         import torch
         import torch.distributed as dist
         dist.all_reduce(self._token, group=self.group)
-        torch.cuda.current_stream().synchronize()
+        if not self.stream_ordered:
+            torch.cuda.current_stream().synchronize()
 
     def _peer_done(self):
         from .lib import _cabi
-        _cabi.check(_cabi.L.asora_sync())   # my reads of the neighbours' memory are complete before I enter the next collective
+        if not self.stream_ordered:
+            _cabi.check(_cabi.L.asora_sync())   # my reads of the neighbours' memory are complete before I enter the next collective
 
     def _peer_halo(self, buf, nb, first_plane, add):
         from .lib import _cabi
@@ -231,7 +236,8 @@ class SlabHalo:
         h, n = self.h, self.h * self.plane
         if self._peer is not None:
             from .lib import _cabi
-            _cabi.check(_cabi.L.asora_sync())                                      # my sweep has finished ...
+            if not self.stream_ordered:
+                _cabi.check(_cabi.L.asora_sync())                                  # my sweep has finished ...
             self._rank_barrier()                                                   # ... and so has everybody's
             self._peer_halo(_cabi.BUF_PHI_ION, self.right, self.hi - h, True)      # the right neighbour's left halo = my last h planes
             self._peer_halo(_cabi.BUF_PHI_ION, self.left, self.lo, True)           # the left neighbour's right halo = my first h planes
@@ -253,9 +259,11 @@ class SlabHalo:
             from .lib import _cabi
             import torch
             if synced:
-                torch.cuda.current_stream().synchronize()   # the caller's collective has completed here
+                if not self.stream_ordered:
+                    torch.cuda.current_stream().synchronize()   # the caller's collective has completed here
             else:
-                _cabi.check(_cabi.L.asora_sync())
+                if not self.stream_ordered:
+                    _cabi.check(_cabi.L.asora_sync())
                 self._rank_barrier()
             self._peer_halo(_cabi.BUF_XH_AV, self.right, self.hi, False)
             self._peer_halo(_cabi.BUF_XH_AV, self.left, self.lo - h, False)
