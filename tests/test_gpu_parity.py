@@ -479,3 +479,31 @@ def test_evolve3D_fortran_ordered_grids(libs):
     assert xf.flags.f_contiguous and not xf.flags.c_contiguous and xc.flags.c_contiguous
     np.testing.assert_allclose(xf, xc, rtol=1e-12, atol=0)
     _assert_close(pf.ravel(), pc.ravel(), "phi_ion F vs C", rtol=1e-11)
+
+
+def test_same_positions_new_fluxes_reuse_the_source_order():
+    """source_data_to_device with the positions of the previous upload only refreshes the fluxes (the Morton order is
+    remembered): the rates must follow the new fluxes, source by source."""
+    import oracle
+    from pyc2ray_b200.lib import _cabi, libasora
+    from tests.fields import make_case
+    c = make_case("multi_n32")
+    _setup(libasora, c)
+    try:
+        first, _, _ = _sweep(libasora, _cabi, c, 0)
+        flux2 = np.ascontiguousarray(c["flux_flat"][::-1] * np.linspace(0.5, 3.0, c["flux_flat"].size))
+        libasora.source_data_to_device(c["pos_flat"], flux2, flux2.size)      # same positions: the cached order is used
+        c2 = dict(c, flux_flat=flux2)
+        second, _, _ = _sweep(libasora, _cabi, c2, 0)
+        pos3 = c["pos_flat"].copy()
+        pos3[:3] = (pos3[:3] + 5) % c["N"]                                    # one source moved: a fresh sort
+        libasora.source_data_to_device(pos3, flux2, flux2.size)
+        c3 = dict(c2, pos_flat=pos3)
+        third, _, _ = _sweep(libasora, _cabi, c3, 0)
+    finally:
+        libasora.device_close()
+    for cc, got, what in ((c, first, "first upload"), (c2, second, "same positions, new fluxes"), (c3, third, "one source moved")):
+        ref, _, _ = oracle.asora_do_all_sources(cc["R"], cc["sig"], cc["dr"], cc["ndens"].ravel(), cc["xh"].ravel(), cc["pos_flat"],
+                                                cc["flux_flat"], cc["N"], cc["thin"], cc["thick"], cc["minlogtau"], cc["dlogtau"],
+                                                cc["NumTau"])
+        _assert_close(got, ref, what)
