@@ -795,6 +795,9 @@ def main():
                     slab["speedup"] = t1 / slab["ms"]
                     slab["efficiency_vs_1gpu"] = t1 / slab["ms"] / world
                     strong["fixed_256"]["slab"] = slab
+                best_ms = min(tn, slab["ms"]) if slab is not None else tn
+                strong["fixed_256"]["best"] = {"decomposition": "slab" if (slab is not None and slab["ms"] < tn) else "list",
+                                               "ms": best_ms, "efficiency_vs_1gpu": t1 / best_ms / world}
             libasora.source_data_to_device(pos_flat, flux_flat, args.nsrc)
 
         # ---- parity: the first 8 sources of rank 0's inputs, default launch shape, against the reference ----------
